@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- interactions/sec of the ALS training hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (our CUDA path; N>1 under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   (CPU reference arm: the restated oracle)
+
+A "step" is one ALS iteration (user half-epoch + item half-epoch, Gram precompute included) over the
+synthetic CSR of BASELINE.json configs[1]: ALS d=128 on 10M x 1M, 1B nnz (SURVEY.md 8d generator C2).
+`value` = nnz * steps / device time with everything resident in HBM; `e2e` = the same iteration driven
+through the reference-facing host-pointer C ABI (bfl_als_partial_update: pinned-host CSR chunks H2D,
+updated factor rows D2H inside the timed region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: users, items, nnz, d, mean degree generator
+    "c2": dict(users=10_000_000, items=1_000_000, nnz=1_000_000_000, d=128,
+               desc="ALS d=128 10Mx1M 1B-nnz synthetic CSR (BASELINE configs[1])"),
+    "c2_small": dict(users=1_000_000, items=100_000, nnz=100_000_000, d=128,
+                     desc="1/10-scale C2 (debug only; NOT the headline workload)"),
+    "tiny": dict(users=20_000, items=5_000, nnz=1_000_000, d=128, desc="smoke-scale (debug only)"),
+}
+ALS_OPT = dict(d=128, optimizer="manual_cg", num_workers=1, compute_loss_on_training=False, alpha=8.0, reg_u=0.1,
+               reg_i=0.1, block_size=32, adaptive_reg=False, num_cg_max_iters=3, eps=1e-10, cg_tolerance=1e-10,
+               num_iters=1)  # d>=128 => iALS++ (als.cc:46); options of benchmark/test_performance.py:18-22
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# workload (generated on the device; torch is plumbing only)
+# ------------------------------------------------------------------------------------------------
+def make_workload(w, device, seed=2024):
+    """Row degrees ~ clipped lognormal (mean nnz/users, max 10k), items uniform, keys sorted within rows
+    (the reference sorts by (row, col), fileio.hpp:330-341), values 1.0.  Returns dict of device tensors:
+    rowwise (indptr_end, keys), colwise (indptr_end, keys), shared vals."""
+    import torch
+    U, I, nnz = w["users"], w["items"], w["nnz"]
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    sigma = 1.0
+    mu = np.log(nnz / U) - 0.5 * sigma * sigma
+    deg = torch.exp(torch.randn(U, device=device, generator=g, dtype=torch.float32) * sigma + mu)
+    deg = torch.clamp(deg, max=10000.0)
+    deg = torch.clamp((deg * (nnz / float(deg.sum().item()))).round().to(torch.int64), min=0)
+    diff = int(nnz - int(deg.sum().item()))
+    if diff != 0:  # spread the rounding remainder over the first |diff| rows with room
+        idx = torch.nonzero(deg > (1 if diff < 0 else 0))[: abs(diff), 0]
+        deg[idx] += 1 if diff > 0 else -1
+    nnz = int(deg.sum().item())
+    rows = torch.repeat_interleave(torch.arange(U, device=device, dtype=torch.int64), deg)
+    cols = torch.randint(0, I, (nnz,), device=device, generator=g, dtype=torch.int64)
+    key = rows * I + cols
+    del rows, cols
+    key = torch.sort(key).values
+    r_keys = (key % I).to(torch.int32)
+    rows = key // I
+    del key
+    r_indptr = torch.cumsum(deg, 0)
+    key2 = r_keys.to(torch.int64) * U + rows
+    del rows
+    key2 = torch.sort(key2).values
+    c_keys = (key2 % U).to(torch.int32)
+    c_cols = key2 // U
+    del key2
+    c_indptr = torch.cumsum(torch.bincount(c_cols, minlength=I), 0)
+    del c_cols
+    vals = torch.ones(nnz, device=device, dtype=torch.float32)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return dict(U=U, I=I, nnz=nnz, r_indptr=r_indptr, r_keys=r_keys, c_indptr=c_indptr, c_keys=c_keys, vals=vals)
+
+
+def init_factors_t(rows, d, device, seed):
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    # abs(N(0, 1/d^2)) (buffalo/algo/als.py:85-86)
+    return torch.abs(torch.randn(rows, d, device=device, generator=g, dtype=torch.float32) * (1.0 / d ** 2)).contiguous()
+
+
+def algorithmic_bytes(nnz, rows, d):
+    """per nnz 4d + 8 (opposite row + key + val); per updated row 12d + 8
+    (indptr, warm-start read, write; the Gram read belongs to the precompute kernel)."""
+    return nnz * (4 * d + 8) + rows * (12 * d + 8)
+
+
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception as e:  # nvidia-smi missing
+            log("clock sampler unavailable:", e)
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower() == "active":
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the restated oracle on the host cores (the reference cannot be built here)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_inputs(wl, Ph, Qh, frac_rows_u, frac_rows_i):
+    """Bounded sample of the SAME workload: the first rows of each orientation against the FULL opposite
+    factor matrix (what SURVEY.md 8d / BASELINE.md section 3 prescribe)."""
+    out = {}
+    for axis, (ind, keys, rows_total, frac) in enumerate([(wl["r_indptr"], wl["r_keys"], wl["U"], frac_rows_u),
+                                                          (wl["c_indptr"], wl["c_keys"], wl["I"], frac_rows_i)]):
+        n_rows = max(1, int(rows_total * frac))
+        hind = ind[:n_rows].cpu().numpy().astype(np.int64)
+        n = int(hind[-1])
+        out[axis] = dict(rows=n_rows, indptr=hind, keys=keys[:n].cpu().numpy(), vals=np.ones(n, np.float32), nnz=n)
+    out["P"] = Ph
+    out["Q"] = Qh
+    return out
+
+
+def cpu_run(sample, opt, cores):
+    """One bounded CPU 'step': Gram + row solves for the sampled rows of both orientations. Returns (seconds, nnz)."""
+    import oracle
+    o = oracle.OracleALS()
+    o.init(dict(opt, num_workers=cores))
+    # the oracle updates the sampled rows in place (like training does); the opposite matrix is the full one
+    o.initialize_model(sample["P"], sample["Q"])
+    t0 = time.perf_counter()
+    nn = 0
+    for axis in (0, 1):
+        s = sample[axis]
+        o.precompute(axis)
+        o.partial_update(0, s["rows"], s["indptr"], s["keys"], s["vals"], axis)
+        nn += s["nnz"]
+    return time.perf_counter() - t0, nn
+
+
+def size_cpu_sample(wl, Ph, Qh, opt, cores, target_s):
+    """Pick row fractions so one CPU step lasts about target_s seconds (probe with a tiny slice first)."""
+    probe = cpu_sample_inputs(wl, Ph, Qh, 2e-4, 2e-4)
+    t, nn = cpu_run(probe, opt, cores)
+    # Gram precompute is a fixed cost per step; estimate it separately
+    import oracle
+    o = oracle.OracleALS()
+    o.init(dict(opt, num_workers=cores))
+    o.initialize_model(probe["P"], probe["Q"])
+    t0 = time.perf_counter()
+    o.precompute(0)
+    o.precompute(1)
+    tg = time.perf_counter() - t0
+    rate = nn / max(t - tg, 1e-3)  # nnz/s of the solves
+    want = max(target_s - tg, 1.0) * rate
+    frac = min(0.05, max(2e-4, want / (2.0 * wl["nnz"])))
+    return frac, probe
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BFL_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (tuned kernels), 1 generic kernels")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.workload != "c2" or args.impl == "reference", "timing rules: warmup >= 3"
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    w = WORKLOADS[args.workload]
+    d = w["d"]
+    opt = dict(ALS_OPT, d=d, _b200_kernel_mode=args.kernel_mode)
+    cores = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, w, opt, cores)
+
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    from buffalo_b200 import _cabi, backend
+
+    t_setup = time.perf_counter()
+    wl = make_workload(w, device)
+    U, I, nnz = wl["U"], wl["I"], wl["nnz"]
+    P = init_factors_t(U, d, device, 7)
+    Q = init_factors_t(I, d, device, 8)
+    if rank == 0:
+        log("workload built in %.1fs: U=%d I=%d nnz=%d d=%d" % (time.perf_counter() - t_setup, U, I, nnz, d))
+
+    obj = backend.CuALS()
+    assert obj.init(opt), obj.last_error
+    obj.bind_factors(P, Q)
+    obj.bind_csr(0, wl["r_indptr"], wl["r_keys"], wl["vals"])
+    obj.bind_csr(1, wl["c_indptr"], wl["c_keys"], wl["vals"])
+    # contiguous row shards per rank (equal row counts; the collective needs equal pieces)
+    def shard(total):
+        per = (total + world - 1) // world
+        return min(rank * per, total), min((rank + 1) * per, total), per
+    u0, u1, uper = shard(U)
+    i0, i1, iper = shard(I)
+    if world > 1:
+        assert U % world == 0 and I % world == 0, "row counts must divide the world size"
+    stream = torch.cuda.current_stream()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    solve_events = []
+
+    def step(record=False):
+        for axis, (a, b, full) in enumerate([(u0, u1, P), (i0, i1, Q)]):
+            obj.precompute_device(axis)
+            if record:
+                e0, e1 = ev(), ev()
+                e0.record(stream)
+            obj.update_device(axis, a, b)
+            if record:
+                e1.record(stream)
+                solve_events.append((axis, e0, e1))
+            if world > 1:  # the one exchange step per half-epoch: all-gather of the updated shard
+                dist.all_gather_into_tensor(full, full[a:b])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _cabi.lib().bfl_kernel_launch_count()
+    t0e, t1e = ev(), ev()
+    barrier()
+    t0e.record(stream)
+    for _ in range(args.steps):
+        step(record=True)
+    t1e.record(stream)
+    barrier()
+    launches = _cabi.lib().bfl_kernel_launch_count() - launches0
+    ms = t0e.elapsed_time(t1e)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = nnz * args.steps / (ms / 1e3)
+
+    # dominant kernel: the row-solve launches (one per half-epoch and rank)
+    per_axis_ms = {0: [], 1: []}
+    for axis, e0, e1 in solve_events:
+        per_axis_ms[axis].append(e0.elapsed_time(e1))
+    peak, peak_src = measured_peak()
+    my_nnz = [int(wl["r_indptr"][u1 - 1].item() - (wl["r_indptr"][u0 - 1].item() if u0 else 0)),
+              int(wl["c_indptr"][i1 - 1].item() - (wl["c_indptr"][i0 - 1].item() if i0 else 0))]
+    my_rows = [u1 - u0, i1 - i0]
+    alg_bytes = [algorithmic_bytes(my_nnz[a], my_rows[a], d) for a in (0, 1)]
+    t_solve = sum(np.mean(per_axis_ms[a]) for a in (0, 1)) / 1e3
+    achieved = sum(alg_bytes) / t_solve / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "ALS row-solve (user + item launches of one iteration)",
+                "algorithmic_bytes_per_launch": {"user_pass": alg_bytes[0], "item_pass": alg_bytes[1]},
+                "launch_ms": {"user_pass": float(np.mean(per_axis_ms[0])), "item_pass": float(np.mean(per_axis_ms[1]))},
+                "share_of_step": t_solve * 1e3 * args.steps / ms}
+
+    out = {"metric": "interactions/sec (nnz/s) ALS d=128", "value": value, "unit": "nnz/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": w["desc"], "users": U, "items": I, "nnz": nnz, "d": d, "optimizer": "ialspp (d>=128)",
+                      "parallelism": "row-sharded x%d, all-gather of updated factor shard per half-epoch" % world,
+                      "l2_policy": "inputs (>= 16 GB) larger than L2; no explicit flush"},
+           "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
+
+    if world == 1 and not args.no_e2e:
+        out["e2e"] = e2e_host_path(args, wl, opt, d, device, P, Q)
+    elif world > 1 and not args.no_e2e:
+        out["e2e"] = {"value": None, "unit": "nnz/s", "note": "host-pointer path is single-GPU (reference ABI); see N=1"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            out["cpu_baseline"] = cpu_baseline(args, wl, P, Q, opt, cores)
+        except Exception as e:  # the oracle is test infrastructure; never fail the bench on it
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def e2e_host_path(args, wl, opt, d, device, Pd, Qd):
+    """The same ALS iteration through the reference-facing C ABI with HOST buffers
+    (init / initialize_model / set_placeholder / precompute / partial_update per chunk), pinned memory,
+    H2D of every chunk's keys+vals and D2H of the updated rows inside the timed region."""
+    import torch
+    from buffalo_b200 import backend
+    U, I, nnz = wl["U"], wl["I"], wl["nnz"]
+    pin = lambda t: t.cpu().pin_memory()  # noqa: E731
+    t0 = time.perf_counter()
+    h = {"r_indptr": wl["r_indptr"].cpu().numpy(), "c_indptr": wl["c_indptr"].cpu().numpy(),
+         "r_keys": pin(wl["r_keys"]), "c_keys": pin(wl["c_keys"]), "vals": pin(wl["vals"])}
+    P = Pd.cpu().pin_memory()
+    Q = Qd.cpu().pin_memory()
+    obj = backend.CuALS()
+    assert obj.init(opt)
+    obj.initialize_model(P.numpy(), Q.numpy())
+    # BufferedDataMatrix semantics: row-aligned chunks of <= limit nnz (buffered_data.py:47-118), batch_mb=4098
+    limit = int(4098 * 1024 * 1024 / 16 / 2)
+    obj.set_placeholder(h["r_indptr"], h["c_indptr"], limit)
+    log("e2e host staging %.1fs" % (time.perf_counter() - t0))
+
+    def chunks(indptr):
+        out, start, rows = [], 0, len(indptr)
+        while start < rows:
+            beg = 0 if start == 0 else int(indptr[start - 1])
+            nxt = int(np.searchsorted(indptr, beg + limit, side="right"))
+            nxt = min(max(nxt, start + 1), rows)
+            out.append((start, nxt, beg, int(indptr[nxt - 1])))
+            start = nxt
+        return out
+    plan = [(0, chunks(h["r_indptr"]), h["r_indptr"], h["r_keys"].numpy()),
+            (1, chunks(h["c_indptr"]), h["c_indptr"], h["c_keys"].numpy())]
+    vals = h["vals"].numpy()
+
+    def step():
+        for axis, cks, indptr, keys in plan:
+            obj.precompute(axis)
+            for (a, b, beg, end) in cks:
+                obj.partial_update(a, b, indptr, keys[beg:end], vals[beg:end], axis)
+    step()  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": nnz * args.steps / dt, "unit": "nnz/s", "h2d_bytes_per_step": int(2 * nnz * 8),
+            "d2h_bytes_per_step": int((U + I) * d * 4), "ms_per_step": dt * 1e3 / args.steps,
+            "api": "bfl_als_partial_update (host CSR chunks, pinned)", "chunks_per_step": len(plan[0][1]) + len(plan[1][1])}
+
+
+def cpu_baseline(args, wl, P, Q, opt, cores):
+    import oracle
+    oracle.build()
+    Ph, Qh = P.cpu().numpy(), Q.cpu().numpy()
+    frac, _ = size_cpu_sample(wl, Ph, Qh, opt, cores, args.cpu_seconds)
+    sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
+    t, nn = cpu_run(sample, opt, cores)
+    return {"value": nn / t, "unit": "nnz/s", "cores": cores, "kind": "port",
+            "sample": "first %.4f%% of user rows and of item rows (%d nnz) against the full opposite factors, "
+                      "Gram precompute of both full matrices included; %.1f s" % (frac * 100, nn, t),
+            "seconds": t}
+
+
+def reference_arm(args, w, opt, cores):
+    """CPU arm: the restated reference path (oracle port; oracle/_ref cannot be built) on all host
+    cores, each step a bounded sample of the same workload."""
+    import torch
+    import oracle
+    oracle.build()
+    device = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    if device.type == "cpu":
+        w = dict(w)
+        log("no GPU for workload generation: CPU generation of a 1/50 slice of the workload")
+        scale = 50
+        w.update(users=w["users"] // scale, nnz=w["nnz"] // scale)
+    wl = make_workload(w, device) if device.type == "cuda" else make_workload_cpu(w)
+    d = w["d"]
+    P = init_factors_t(wl["U"], d, device, 7)
+    Q = init_factors_t(wl["I"], d, device, 8)
+    Ph, Qh = P.cpu().numpy(), Q.cpu().numpy()
+    frac, _ = size_cpu_sample(wl, Ph, Qh, opt, cores, args.cpu_seconds)
+    sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
+    del wl
+    for _ in range(min(args.warmup, 1)):
+        cpu_run(sample, opt, cores)
+    tt, nn = 0.0, 0
+    for _ in range(args.steps):
+        t, n = cpu_run(sample, opt, cores)
+        tt += t
+        nn += n
+    v = nn / tt
+    desc = ("each step: first %.4f%% of user rows and item rows (%d nnz) vs full opposite factors, Gram of both "
+            "full matrices included" % (frac * 100, nn // args.steps))
+    out = {"impl": "reference", "metric": "interactions/sec (nnz/s) ALS d=128", "value": v, "unit": "nnz/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": tt * 1e3 / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": w["desc"], "users": w["users"], "items": w["items"], "nnz": w["nnz"], "d": d,
+                      "optimizer": "ialspp (d>=128)", "sampled": desc},
+           "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": cores, "kind": "port", "sample": desc},
+           "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def make_workload_cpu(w, seed=2024):
+    import torch
+    rng = np.random.default_rng(seed)
+    U, I, nnz = w["users"], w["items"], w["nnz"]
+    deg = np.minimum(np.exp(rng.normal(np.log(nnz / U) - 0.5, 1.0, U)), 10000)
+    deg = np.maximum((deg * nnz / deg.sum()).round().astype(np.int64), 0)
+    nnz = int(deg.sum())
+    rows = np.repeat(np.arange(U), deg)
+    cols = rng.integers(0, I, nnz)
+    key = np.sort(rows * I + cols)
+    r_keys = (key % I).astype(np.int32)
+    rows = key // I
+    key2 = np.sort(r_keys.astype(np.int64) * U + rows)
+    t = torch.from_numpy
+    return dict(U=U, I=I, nnz=nnz, r_indptr=t(np.cumsum(deg)), r_keys=t(r_keys),
+                c_indptr=t(np.cumsum(np.bincount(key2 // U, minlength=I))), c_keys=t((key2 % U).astype(np.int32)),
+                vals=torch.ones(nnz))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

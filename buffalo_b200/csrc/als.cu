@@ -1,0 +1,341 @@
+// ALS backend: host-side state machine + C ABI (see include/buffalo_b200.h).
+// Replaces als::CALS (lib/algo_impl/als/als.cc) / cuda_als::CuALS (lib/cuda/als/als.cu).
+#include "als_fast.cuh"
+#include "als_generic.cuh"
+#include "bfl_common.cuh"
+
+using namespace bfl;
+
+struct bfl_als {
+    // options (als.cc:30-69)
+    bool opt_set = false;
+    int d = 0, vdim = 0;
+    int num_cg_max_iters = 3;
+    int optimizer_code = 2;  // 0 llt, 1 ldlt, 2 manual_cg, 8 ialspp
+    int block_size = 32;
+    bool adaptive_reg = false, compute_loss = true;
+    float alpha = 8.f, reg_u = 0.1f, reg_i = 0.1f, eps = 1e-10f, cg_tolerance = 1e-10f;
+    int kernel_mode = 0;  // 0 auto (tuned kernels when applicable), 1 force generic
+
+    // factors: either owned device mirrors of retained host pointers, or borrowed device memory
+    float* hostP = nullptr;
+    float* hostQ = nullptr;
+    DevBuf<float> ownP, ownQ;
+    float* dP = nullptr;
+    float* dQ = nullptr;
+    int64_t P_rows = 0, Q_rows = 0;
+    bool factors_ready = false;
+
+    // CSR per axis
+    DevBuf<int64_t> own_indptr[2];
+    const int64_t* d_indptr[2] = {nullptr, nullptr};
+    DevBuf<int32_t> stage_keys;
+    DevBuf<float> stage_vals;
+    const int32_t* d_keys[2] = {nullptr, nullptr};  // resident CSR (device path)
+    const float* d_vals[2] = {nullptr, nullptr};
+    int64_t csr_rows[2] = {0, 0}, csr_nnz[2] = {0, 0};
+    bool ph_set = false;
+
+    DevBuf<float> G;          // d x d
+    DevBuf<float> gram_part;  // partials of the two-stage Gram
+    DevBuf<float> yui;        // generic ialspp scratch
+    DevBuf<double> d_loss;    // 2 doubles
+    DevBuf<int32_t> bins;     // row lists of the tuned path
+    DevBuf<int32_t> bin_counts;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+};
+
+namespace {
+
+int als_apply_options(bfl_als* h, const JsonOpt& j) {
+    h->d = j.integer("d", 20);
+    if (h->d <= 0 || h->d > 512) BFL_FAIL(BFL_ERR_OPTION, "d must be in [1, 512], got " + std::to_string(h->d));
+    h->vdim = (h->d + 3) / 4 * 4;
+    h->num_cg_max_iters = j.integer("num_cg_max_iters", 3);
+    h->block_size = j.integer("block_size", 32);
+    if (h->block_size <= 0) BFL_FAIL(BFL_ERR_OPTION, "block_size must be positive");
+    h->adaptive_reg = j.flag("adaptive_reg", false);
+    h->compute_loss = j.flag("compute_loss_on_training", true);
+    h->alpha = (float)j.number("alpha", 8.0);
+    h->reg_u = (float)j.number("reg_u", 0.1);
+    h->reg_i = (float)j.number("reg_i", 0.1);
+    h->eps = (float)j.number("eps", 1e-10);
+    h->cg_tolerance = (float)j.number("cg_tolerance", 1e-10);
+    h->kernel_mode = j.integer("_b200_kernel_mode", 0);
+    std::string optimizer = j.string("optimizer", "manual_cg");
+    if (h->d >= 128) optimizer = "ialspp";  // als.cc:46
+    if (optimizer == "llt") h->optimizer_code = 0;
+    else if (optimizer == "ldlt") h->optimizer_code = 1;
+    else if (optimizer == "manual_cg") h->optimizer_code = 2;
+    else if (optimizer == "ialspp") h->optimizer_code = 8;
+    else
+        BFL_FAIL(BFL_ERR_OPTION, "optimizer '" + optimizer +
+                                     "' is not available on the B200 backend (supported: llt, ldlt, manual_cg, ialspp)");
+    if (BFL_OK != require_device()) return BFL_ERR_CUDA;
+    int dev = 0;
+    BFL_CUDA(cudaGetDevice(&dev));
+    BFL_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (!h->stream) BFL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (BFL_OK != h->G.reserve((size_t)h->d * h->d)) return BFL_ERR_CUDA;
+    if (BFL_OK != h->d_loss.reserve(2)) return BFL_ERR_CUDA;
+    h->opt_set = true;
+    return BFL_OK;
+}
+
+int gram(bfl_als* h, const float* F, int64_t rows, cudaStream_t st) {
+    const int D = h->d;
+    const int nslab = (D + 127) / 128;
+    int64_t ntiles = (rows + GRAM_TR - 1) / GRAM_TR;
+    int gx = (int)std::min<int64_t>(std::max<int64_t>(ntiles, 1), (int64_t)h->num_sms * 2 / (nslab * nslab) + 1);
+    if (BFL_OK != h->gram_part.reserve((size_t)gx * nslab * nslab * 128 * 128)) return BFL_ERR_CUDA;
+    dim3 grid(gx, nslab * nslab);
+    gram_partial_kernel<<<grid, GRAM_THREADS, 0, st>>>(F, rows, D, h->vdim, h->gram_part.p, nslab);
+    BFL_LAUNCHED();
+    gram_reduce_kernel<<<(D * D + 255) / 256, 256, 0, st>>>(h->gram_part.p, gx, nslab, D, h->G.p);
+    BFL_LAUNCHED();
+    return BFL_OK;
+}
+
+template <int NC>
+int launch_generic(bfl_als* h, const AlsArgs& a, int64_t nrows, cudaStream_t st) {
+    int grid = (int)std::min<int64_t>((nrows + GEN_WARPS - 1) / GEN_WARPS, (int64_t)h->num_sms * 8);
+    if (grid < 1) grid = 1;
+    if (h->optimizer_code == 8)
+        als_ialspp_warp_kernel<NC><<<grid, GEN_WARPS * 32, 0, st>>>(a);
+    else
+        als_cg_warp_kernel<NC><<<grid, GEN_WARPS * 32, 0, st>>>(a);
+    BFL_LAUNCHED();
+    return BFL_OK;
+}
+
+// Solve rows [row_begin,row_end) of axis with keys/vals device buffers whose element 0 is global
+// offset `shift`.  chunk_nnz = number of entries those rows span.
+int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const int32_t* keys, const float* vals,
+               int64_t shift, int64_t chunk_nnz, double* d_loss, cudaStream_t st) {
+    if (row_end <= row_begin) return BFL_OK;
+    AlsArgs a;
+    a.X = axis == 0 ? h->dP : h->dQ;
+    a.Y = axis == 0 ? h->dQ : h->dP;
+    a.G = h->G.p;
+    a.indptr = h->d_indptr[axis];
+    a.keys = keys;
+    a.vals = vals;
+    a.yui = nullptr;
+    a.loss = d_loss;
+    a.row_list = nullptr;
+    a.shift = shift;
+    a.row_begin = row_begin;
+    a.row_end = row_end;
+    a.Y_rows = axis == 0 ? h->Q_rows : h->P_rows;
+    a.D = h->d;
+    a.ld = h->vdim;
+    a.block_size = h->block_size;
+    a.max_iters = h->num_cg_max_iters;
+    a.adaptive_reg = h->adaptive_reg;
+    a.compute_loss = h->compute_loss;
+    a.axis = axis;
+    a.alpha = h->alpha;
+    a.reg = axis == 0 ? h->reg_u : h->reg_i;
+    a.eps = h->eps;
+    a.tol = h->cg_tolerance;
+    const int64_t nrows = row_end - row_begin;
+
+    if (h->kernel_mode == 0 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
+        return fast_als_launch(a, h->optimizer_code, h->num_sms, h->bins, h->bin_counts, st);
+    }
+
+    if (h->optimizer_code == 0 || h->optimizer_code == 1) {
+        const size_t smem = ((size_t)h->d * (h->d + 1) + 2 * h->d + (size_t)DIRECT_NB * h->d) * sizeof(float);
+        if (smem > 220 * 1024) BFL_FAIL(BFL_ERR_OPTION, "llt/ldlt needs d <= 224 on this backend");
+        BFL_CUDA(cudaFuncSetAttribute(als_direct_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = (int)std::min<int64_t>(nrows, (int64_t)h->num_sms * 4);
+        als_direct_cta_kernel<<<grid, DIRECT_THREADS, smem, st>>>(a);
+        BFL_LAUNCHED();
+        return BFL_OK;
+    }
+    if (h->optimizer_code == 8) {
+        if (BFL_OK != h->yui.reserve((size_t)std::max<int64_t>(chunk_nnz, 1))) return BFL_ERR_CUDA;
+        a.yui = h->yui.p;
+    }
+    const int nc = (h->d + 31) / 32;
+    if (nc <= 1) return launch_generic<1>(h, a, nrows, st);
+    if (nc <= 2) return launch_generic<2>(h, a, nrows, st);
+    if (nc <= 4) return launch_generic<4>(h, a, nrows, st);
+    if (nc <= 8) return launch_generic<8>(h, a, nrows, st);
+    return launch_generic<16>(h, a, nrows, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+bfl_als_t* bfl_als_create(void) { return new (std::nothrow) bfl_als(); }
+
+void bfl_als_destroy(bfl_als_t* h) {
+    if (!h) return;
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bfl_als_init(bfl_als_t* h, const char* opt_path) {
+    if (!h || !opt_path) BFL_FAIL(BFL_ERR_ARG, "null argument");
+    JsonOpt j;
+    std::string err;
+    if (!j.load(opt_path, &err)) BFL_FAIL(BFL_ERR_OPTION, err);
+    return als_apply_options(h, j);
+}
+
+int bfl_als_init_json(bfl_als_t* h, const char* json_text) {
+    if (!h || !json_text) BFL_FAIL(BFL_ERR_ARG, "null argument");
+    JsonOpt j;
+    std::string err;
+    if (!j.parse(json_text, &err)) BFL_FAIL(BFL_ERR_OPTION, "Failed to parse: " + err);
+    return als_apply_options(h, j);
+}
+
+int bfl_als_get_vdim(bfl_als_t* h) { return h ? h->vdim : 0; }
+
+int bfl_als_initialize_model(bfl_als_t* h, float* P, int32_t P_rows, float* Q, int32_t Q_rows) {
+    if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before initialize_model()");
+    if (!P || !Q || P_rows <= 0 || Q_rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad factor arguments");
+    h->hostP = P;
+    h->hostQ = Q;
+    h->P_rows = P_rows;
+    h->Q_rows = Q_rows;
+    if (BFL_OK != h->ownP.reserve((size_t)P_rows * h->vdim)) return BFL_ERR_CUDA;
+    if (BFL_OK != h->ownQ.reserve((size_t)Q_rows * h->vdim)) return BFL_ERR_CUDA;
+    h->dP = h->ownP.p;
+    h->dQ = h->ownQ.p;
+    BFL_CUDA(cudaMemcpyAsync(h->dP, P, sizeof(float) * (size_t)P_rows * h->vdim, cudaMemcpyHostToDevice, h->stream));
+    BFL_CUDA(cudaMemcpyAsync(h->dQ, Q, sizeof(float) * (size_t)Q_rows * h->vdim, cudaMemcpyHostToDevice, h->stream));
+    BFL_CUDA(cudaStreamSynchronize(h->stream));
+    h->factors_ready = true;
+    return BFL_OK;
+}
+
+int bfl_als_set_placeholder(bfl_als_t* h, const int64_t* lindptr, const int64_t* rindptr, size_t batch_size) {
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "initialize_model() must precede set_placeholder()");
+    if (!lindptr || !rindptr) BFL_FAIL(BFL_ERR_ARG, "null indptr");
+    if (BFL_OK != h->own_indptr[0].reserve((size_t)h->P_rows)) return BFL_ERR_CUDA;
+    if (BFL_OK != h->own_indptr[1].reserve((size_t)h->Q_rows)) return BFL_ERR_CUDA;
+    BFL_CUDA(cudaMemcpyAsync(h->own_indptr[0].p, lindptr, sizeof(int64_t) * h->P_rows, cudaMemcpyHostToDevice, h->stream));
+    BFL_CUDA(cudaMemcpyAsync(h->own_indptr[1].p, rindptr, sizeof(int64_t) * h->Q_rows, cudaMemcpyHostToDevice, h->stream));
+    h->d_indptr[0] = h->own_indptr[0].p;
+    h->d_indptr[1] = h->own_indptr[1].p;
+    if (batch_size) {
+        if (BFL_OK != h->stage_keys.reserve(batch_size)) return BFL_ERR_CUDA;
+        if (BFL_OK != h->stage_vals.reserve(batch_size)) return BFL_ERR_CUDA;
+    }
+    BFL_CUDA(cudaStreamSynchronize(h->stream));
+    h->ph_set = true;
+    return BFL_OK;
+}
+
+int bfl_als_precompute(bfl_als_t* h, int axis) {
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "initialize_model() must precede precompute()");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    const float* F = axis == 0 ? h->dQ : h->dP;
+    const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
+    int rc = gram(h, F, rows, h->stream);
+    if (rc != BFL_OK) return rc;
+    BFL_CUDA(cudaStreamSynchronize(h->stream));
+    return BFL_OK;
+}
+
+int bfl_als_partial_update(bfl_als_t* h, int32_t start_x, int32_t next_x, const int64_t* indptr,
+                           const int32_t* keys, const float* vals, int axis, double* loss_nume,
+                           double* loss_deno) {
+    if (loss_nume) *loss_nume = 0.0;
+    if (loss_deno) *loss_deno = 0.0;
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "initialize_model() must precede partial_update()");
+    if (!h->hostP) BFL_FAIL(BFL_ERR_STATE, "partial_update() is the host-pointer path; use bfl_als_update_device with bound device factors");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    if (next_x - start_x == 0) return BFL_OK;  // als.cc:115-118
+    const int64_t rows = axis == 0 ? h->P_rows : h->Q_rows;
+    if (start_x < 0 || next_x > rows || next_x < start_x || !indptr || !keys || !vals)
+        BFL_FAIL(BFL_ERR_ARG, "bad chunk arguments");
+    if (!h->ph_set || h->d_indptr[axis] != h->own_indptr[axis].p) {
+        // the CPU holder needs no set_placeholder (als.py:156-158 only calls it for the accelerator);
+        // upload this axis' end offsets on first use
+        if (BFL_OK != h->own_indptr[axis].reserve((size_t)rows)) return BFL_ERR_CUDA;
+        BFL_CUDA(cudaMemcpyAsync(h->own_indptr[axis].p, indptr, sizeof(int64_t) * rows, cudaMemcpyHostToDevice, h->stream));
+        h->d_indptr[axis] = h->own_indptr[axis].p;
+    }
+    const int64_t beg = start_x == 0 ? 0 : indptr[start_x - 1];
+    const int64_t end = indptr[next_x - 1];
+    const int64_t n = end - beg;
+    if (n > 0) {
+        if (BFL_OK != h->stage_keys.reserve((size_t)n)) return BFL_ERR_CUDA;
+        if (BFL_OK != h->stage_vals.reserve((size_t)n)) return BFL_ERR_CUDA;
+        BFL_CUDA(cudaMemcpyAsync(h->stage_keys.p, keys, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+        BFL_CUDA(cudaMemcpyAsync(h->stage_vals.p, vals, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    }
+    BFL_CUDA(cudaMemsetAsync(h->d_loss.p, 0, 2 * sizeof(double), h->stream));
+    int rc = solve_rows(h, axis, start_x, next_x, h->stage_keys.p, h->stage_vals.p, beg, n, h->d_loss.p, h->stream);
+    if (rc != BFL_OK) return rc;
+    double hl[2] = {0.0, 0.0};
+    BFL_CUDA(cudaMemcpyAsync(hl, h->d_loss.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    // copy the updated rows back into the caller's matrix (als.cu:321-336,403)
+    float* hostF = axis == 0 ? h->hostP : h->hostQ;
+    float* devF = axis == 0 ? h->dP : h->dQ;
+    const size_t off = (size_t)start_x * h->vdim;
+    BFL_CUDA(cudaMemcpyAsync(hostF + off, devF + off, sizeof(float) * (size_t)(next_x - start_x) * h->vdim,
+                             cudaMemcpyDeviceToHost, h->stream));
+    BFL_CUDA(cudaStreamSynchronize(h->stream));
+    if (loss_nume) *loss_nume = hl[0];
+    if (loss_deno) *loss_deno = hl[1];
+    return BFL_OK;
+}
+
+int bfl_als_bind_factors_device(bfl_als_t* h, float* dP, int64_t P_rows, float* dQ, int64_t Q_rows) {
+    if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before binding factors");
+    if (!dP || !dQ || P_rows <= 0 || Q_rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad factor arguments");
+    if (((uintptr_t)dP | (uintptr_t)dQ) & 15) BFL_FAIL(BFL_ERR_ARG, "device factor pointers must be 16-byte aligned");
+    h->hostP = h->hostQ = nullptr;
+    h->ownP.release();
+    h->ownQ.release();
+    h->dP = dP;
+    h->dQ = dQ;
+    h->P_rows = P_rows;
+    h->Q_rows = Q_rows;
+    h->factors_ready = true;
+    return BFL_OK;
+}
+
+int bfl_als_bind_csr_device(bfl_als_t* h, int axis, const int64_t* d_indptr, const int32_t* d_keys,
+                            const float* d_vals, int64_t rows, int64_t nnz) {
+    if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before binding a CSR");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    if (!d_indptr || (nnz > 0 && (!d_keys || !d_vals)) || rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad CSR arguments");
+    h->d_indptr[axis] = d_indptr;
+    h->d_keys[axis] = d_keys;
+    h->d_vals[axis] = d_vals;
+    h->csr_rows[axis] = rows;
+    h->csr_nnz[axis] = nnz;
+    return BFL_OK;
+}
+
+int bfl_als_precompute_device(bfl_als_t* h, int axis, void* stream) {
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "factors not bound");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    const float* F = axis == 0 ? h->dQ : h->dP;
+    const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
+    return gram(h, F, rows, (cudaStream_t)stream);
+}
+
+int bfl_als_update_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end, double* d_loss,
+                          void* stream) {
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "factors not bound");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    if (!h->d_keys[axis] && h->csr_nnz[axis] > 0) BFL_FAIL(BFL_ERR_STATE, "no device CSR bound for this axis");
+    if (!h->d_indptr[axis]) BFL_FAIL(BFL_ERR_STATE, "no device CSR bound for this axis");
+    if (row_begin < 0 || row_end > h->csr_rows[axis] || row_end < row_begin) BFL_FAIL(BFL_ERR_ARG, "bad row range");
+    return solve_rows(h, axis, row_begin, row_end, h->d_keys[axis], h->d_vals[axis], 0, h->csr_nnz[axis], d_loss,
+                      (cudaStream_t)stream);
+}
+
+const float* bfl_als_gram_device(bfl_als_t* h) { return h ? h->G.p : nullptr; }
+float* bfl_als_gram_device_mut(bfl_als_t* h) { return h ? h->G.p : nullptr; }
+
+}  // extern "C"

@@ -581,7 +581,8 @@ ORC_API void orc_bpr_update(const orc_sgd_opt* o, float* P, float* Q, float* Qb,
                 for (int k = 0; k < D; ++k) gradQ[(int64_t)neg * D + k] -= logit * p[k];
                 if (o->use_bias) gradQb[neg] -= logit;
             }
-            if (o->per_coordinate_normalize) { P_cnt[u] += 1; Q_cnt[pos] += 1; }  /* (:174-181), per positive; num_neg==1 */
+            /* (:174-181) once per positive: triples are laid out positive-major, num_neg per positive */
+            if (o->per_coordinate_normalize && (s % o->num_negative_samples) == 0) { P_cnt[u] += 1; Q_cnt[pos] += 1; }
         } else {                                                               /* (:157-171) */
             /* g is a LAZY Eigen expression in the reference (auto, :158): it is evaluated
              * at `P_.row(u) += alpha * g` AFTER q_i and q_j were updated. */

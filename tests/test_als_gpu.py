@@ -1,0 +1,268 @@
+"""ALS parity on the GPU: the CUDA path, driven through the C ABI exactly as the reference's Python
+driver drives `self.obj` (buffalo/algo/als.py:115-142), against the CPU oracle on the same seeded
+inputs and against the committed golden fixtures.
+
+Tolerance: factors within 1e-3 relative max-norm (BASELINE.json north_star), stated per test; both
+sides compute in fp32 with different summation orders.  Loss pieces within 1e-4 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import init_factors, make_csr, rel_err, transpose_csr
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FACTOR_TOL = 1e-3
+
+
+def full_opt(**kw):
+    opt = dict(d=20, optimizer="manual_cg", num_workers=8, compute_loss_on_training=True, alpha=8.0, reg_u=0.1,
+               reg_i=0.1, block_size=32, adaptive_reg=False, num_cg_max_iters=3, eps=1e-10, cg_tolerance=1e-10)
+    opt.update(kw)
+    return opt
+
+
+def gpu_half(opt, P, Q, indptr, keys, vals, axis, chunks=1, placeholder=None):
+    """One half-epoch through the host-pointer C ABI (init / initialize_model / precompute / partial_update)."""
+    from buffalo_b200 import backend
+    obj = backend.CuALS()
+    assert obj.init(opt)
+    vdim = obj.get_vdim()
+    d = opt["d"]
+    Pp = np.zeros((P.shape[0], vdim), np.float32)
+    Qp = np.zeros((Q.shape[0], vdim), np.float32)
+    Pp[:, :d], Qp[:, :d] = P[:, :d], Q[:, :d]
+    obj.initialize_model(Pp, Qp)
+    if placeholder is not None:
+        obj.set_placeholder(placeholder[0], placeholder[1], len(keys))
+    obj.precompute(axis)
+    rows = P.shape[0] if axis == 0 else Q.shape[0]
+    bounds = np.linspace(0, rows, chunks + 1).astype(int)
+    nume = deno = 0.0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        beg = 0 if a == 0 else int(indptr[a - 1])
+        end = int(indptr[b - 1]) if b > 0 else 0
+        k = np.ascontiguousarray(keys[beg:end]) if end > beg else np.zeros(1, np.int32)
+        v = np.ascontiguousarray(vals[beg:end]) if end > beg else np.zeros(1, np.float32)
+        n_, d_ = obj.partial_update(int(a), int(b), indptr, k, v, axis)
+        nume += n_
+        deno += d_
+    X = Pp if axis == 0 else Qp
+    assert not X[:, d:].any(), "padding columns must stay zero"
+    return X[:, :d].copy(), nume, deno
+
+
+def oracle_half(opt, P, Q, indptr, keys, vals, axis):
+    import oracle
+    o = oracle.OracleALS()
+    o.init(opt)
+    P1, Q1 = P.copy(), Q.copy()
+    o.initialize_model(P1, Q1)
+    o.precompute(axis)
+    rows = P.shape[0] if axis == 0 else Q.shape[0]
+    n, dn = o.partial_update(0, rows, indptr, keys, vals, axis)
+    return (P1 if axis == 0 else Q1), n, dn
+
+
+def check_loss(n, dn, n0, dn0):
+    assert abs(n - n0) <= 1e-4 * max(1.0, abs(n0)), (n, n0)
+    assert abs(dn - dn0) <= 1e-4 * max(1.0, abs(dn0)), (dn, dn0)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(GOLDEN, "golden_als.json")))["cases"],
+                         ids=lambda c: c["file"][:-4])
+def test_golden_fixture(cuda_lib, case):
+    z = np.load(os.path.join(GOLDEN, case["file"]))
+    X, n, dn = gpu_half(case["opt"], z["P"], z["Q"], z["indptr"], z["keys"], z["vals"], case["axis"])
+    assert rel_err(X, z["X"]) < FACTOR_TOL
+    check_loss(n, dn, float(z["nume"]), float(z["deno"]))
+
+
+@pytest.mark.parametrize("d,optimizer,kw", [
+    (32, "manual_cg", {}),                       # BASELINE configs[0] shape family (d=32, default optimizer)
+    (32, "manual_cg", {"adaptive_reg": True, "num_cg_max_iters": 5}),
+    (10, "manual_cg", {}), (40, "manual_cg", {}), (80, "manual_cg", {}),   # benchmark D sweep (test_performance.py:9)
+    (5, "llt", {}), (20, "ldlt", {}), (64, "llt", {"adaptive_reg": True}), (96, "ldlt", {}),
+    (100, "ialspp", {"block_size": 7}), (64, "ialspp", {"block_size": 16}), (48, "ialspp", {"block_size": 64}),
+    (128, "manual_cg", {}), (160, "manual_cg", {}), (256, "manual_cg", {}), (128, "llt", {"block_size": 64}),
+])
+def test_parity_vs_oracle(cuda_lib, d, optimizer, kw):
+    U, I, nnz = 3000, 2000, 90000
+    indptr, keys, vals, _ = make_csr(U, I, nnz, seed=d * 7 + len(optimizer), empty_rows=20)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    opt = full_opt(d=d, optimizer=optimizer, **kw)
+    # a state as met after a few ALS iterations: signed factors of moderate size
+    P = init_factors(U, d, d, 1, scale=0.1, signed=True)
+    Q = init_factors(I, d, d, 2, scale=0.1, signed=True)
+    X, n, dn = gpu_half(opt, P, Q, indptr, keys, vals, 0)
+    X0, n0, dn0 = oracle_half(opt, P, Q, indptr, keys, vals, 0)
+    assert rel_err(X, X0) < FACTOR_TOL
+    check_loss(n, dn, n0, dn0)
+    X, n, dn = gpu_half(opt, P, Q, cind, ckeys, cvals, 1)
+    X0, n0, dn0 = oracle_half(opt, P, Q, cind, ckeys, cvals, 1)
+    assert rel_err(X, X0) < FACTOR_TOL
+    check_loss(n, dn, n0, dn0)
+
+
+def test_c1_config_training_trajectory(cuda_lib):
+    """BASELINE configs[0]: ALS d=32 on 10k x 5k, 200k nnz, default options, from the reference's own
+    initialisation abs(N(0, 1/d^2)) (als.py:85-86): three full iterations, GPU and oracle advanced side by
+    side from their own states; factors and RMSE must agree at every iteration."""
+    U, I, nnz, d = 10000, 5000, 200000, 32
+    indptr, keys, vals, _ = make_csr(U, I, nnz, seed=1234)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    opt = full_opt(d=d)
+    Pg = init_factors(U, d, d, 7)
+    Qg = init_factors(I, d, d, 8)
+    Po, Qo = Pg.copy(), Qg.copy()
+    for it in range(3):
+        Pg, n1, d1 = gpu_half(opt, Pg, Qg, indptr, keys, vals, 0)
+        Qg, n2, d2 = gpu_half(opt, Pg, Qg, cind, ckeys, cvals, 1)
+        Po, m1, e1 = oracle_half(opt, Po, Qo, indptr, keys, vals, 0)
+        Qo, m2, e2 = oracle_half(opt, Po, Qo, cind, ckeys, cvals, 1)
+        assert rel_err(Pg, Po) < FACTOR_TOL and rel_err(Qg, Qo) < FACTOR_TOL, it
+        rmse_g = ((n1 + n2) / (d1 + d2 + 1e-10)) ** 0.5     # als.py:171
+        rmse_o = ((m1 + m2) / (e1 + e2 + 1e-10)) ** 0.5
+        assert abs(rmse_g - rmse_o) < 1e-4 * rmse_o
+
+
+def test_chunked_equals_whole_and_placeholder(cuda_lib):
+    # BufferedDataMatrix feeds row-aligned chunks (buffered_data.py:85-118); results must not depend on chunking
+    U, I, nnz, d = 2000, 1500, 60000, 128
+    indptr, keys, vals, _ = make_csr(U, I, nnz, seed=99, empty_rows=30)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    opt = full_opt(d=d)
+    P = init_factors(U, d, d, 1, scale=0.1, signed=True)
+    Q = init_factors(I, d, d, 2, scale=0.1, signed=True)
+    X1, n1, d1 = gpu_half(opt, P, Q, cind, ckeys, cvals, 1, chunks=1)
+    X5, n5, d5 = gpu_half(opt, P, Q, cind, ckeys, cvals, 1, chunks=5, placeholder=(indptr, cind))
+    assert rel_err(X5, X1) < 1e-5
+    check_loss(n5, d5, n1, d1)
+
+
+def test_empty_rows_untouched_and_empty_chunk(cuda_lib):
+    U, I, d = 500, 300, 16
+    indptr, keys, vals, rows = make_csr(U, I, 4000, seed=3, empty_rows=60)
+    P = init_factors(U, d, d, 1, scale=0.1)
+    Q = init_factors(I, d, d, 2, scale=0.1)
+    empty = np.setdiff1d(np.arange(U), rows)
+    for optimizer in ("llt", "manual_cg", "ialspp"):
+        X, _, _ = gpu_half(full_opt(d=d, optimizer=optimizer), P, Q, indptr, keys, vals, 0)
+        assert np.array_equal(X[empty], P[empty])      # als.cc:159-162
+    from buffalo_b200 import backend
+    obj = backend.CuALS()
+    obj.init(full_opt(d=d))
+    Pp, Qp = P.copy(), Q.copy()
+    obj.initialize_model(Pp, Qp)
+    obj.precompute(0)
+    assert obj.partial_update(7, 7, indptr, keys, vals, 0) == (0.0, 0.0)   # als.cc:115-118
+
+
+def test_device_path_equals_host_path(cuda_lib):
+    import torch
+    from buffalo_b200 import backend
+    U, I, nnz, d = 4000, 2500, 150000, 128
+    indptr, keys, vals, _ = make_csr(U, I, nnz, seed=5, empty_rows=11)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    opt = full_opt(d=d)
+    P = init_factors(U, d, d, 1, scale=0.1, signed=True)
+    Q = init_factors(I, d, d, 2, scale=0.1, signed=True)
+    Xh, nh, dh = gpu_half(opt, P, Q, indptr, keys, vals, 0)
+    Yh, mh, eh = gpu_half(opt, Xh, Q, cind, ckeys, cvals, 1)
+    obj = backend.CuALS()
+    obj.init(opt)
+    dev = torch.device("cuda:0")
+    tP, tQ = torch.from_numpy(P).to(dev), torch.from_numpy(Q).to(dev)
+    obj.bind_factors(tP, tQ)
+    obj.bind_csr(0, torch.from_numpy(indptr).to(dev), torch.from_numpy(keys).to(dev), torch.from_numpy(vals).to(dev))
+    obj.bind_csr(1, torch.from_numpy(cind).to(dev), torch.from_numpy(ckeys).to(dev), torch.from_numpy(cvals).to(dev))
+    loss = torch.zeros(2, dtype=torch.float64, device=dev)
+    obj.precompute_device(0)
+    obj.update_device(0, 0, U, loss)
+    l0 = loss.cpu().numpy().copy()
+    loss.zero_()
+    obj.precompute_device(1)
+    obj.update_device(1, 0, I // 2, loss)       # two row ranges = one pass
+    obj.update_device(1, I // 2, I, loss)
+    torch.cuda.synchronize()
+    assert rel_err(tP.cpu().numpy(), Xh) < 1e-5
+    assert rel_err(tQ.cpu().numpy(), Yh) < 1e-5
+    check_loss(l0[0], l0[1], nh, dh)
+    l1 = loss.cpu().numpy()
+    check_loss(l1[0], l1[1], mh, eh)
+
+
+def test_gram_precompute(cuda_lib):
+    import torch
+    from buffalo_b200 import backend
+    for d, rows in [(32, 5000), (100, 3333), (128, 20000), (256, 1000)]:
+        obj = backend.CuALS()
+        obj.init(full_opt(d=d))
+        rng = np.random.default_rng(d)
+        Q = rng.normal(size=(rows, obj.get_vdim())).astype(np.float32)
+        Q[:, d:] = 0
+        tP = torch.zeros(8, obj.get_vdim(), device="cuda")
+        tQ = torch.from_numpy(Q).cuda()
+        obj.bind_factors(tP, tQ)
+        obj.precompute_device(0)
+        torch.cuda.synchronize()
+        G = obj.gram_tensor().cpu().numpy()
+        G0 = Q[:, :d].astype(np.float64).T @ Q[:, :d].astype(np.float64)
+        assert rel_err(G, G0) < 1e-5
+
+
+def test_unsupported_optimizer_and_state_errors(cuda_lib):
+    from buffalo_b200 import _cabi, backend
+    obj = backend.CuALS()
+    assert obj.init(full_opt(optimizer="eigen_cg")) is False        # rejected like an invalid option file
+    assert "eigen_cg" in obj.last_error
+    obj = backend.CuALS()
+    with pytest.raises(_cabi.BackendError):
+        obj.precompute(0)                                            # before init/initialize_model
+
+
+def test_mid_size_sampled_rows_property(cuda_lib):
+    """Size-independent check at a size the oracle cannot sweep in seconds: solve 1M x 200k, 40M nnz on the
+    device, then re-solve a random sample of rows with the oracle (full opposite factors, sampled CSR rows)."""
+    import torch
+    from buffalo_b200 import backend
+    import oracle
+    dev = torch.device("cuda:0")
+    U, I, nnz, d = 1_000_000, 200_000, 40_000_000, 128
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)
+    rows = torch.randint(0, U, (nnz,), device=dev, generator=g, dtype=torch.int64)
+    cols = torch.randint(0, I, (nnz,), device=dev, generator=g, dtype=torch.int64)
+    key = torch.sort(rows * I + cols).values
+    rows, cols = key // I, (key % I).to(torch.int32)
+    indptr = torch.cumsum(torch.bincount(rows, minlength=U), 0)
+    vals = torch.ones(nnz, device=dev, dtype=torch.float32)
+    P = (torch.randn(U, d, device=dev, generator=g) * 0.05).contiguous()
+    Q = (torch.randn(I, d, device=dev, generator=g) * 0.05).contiguous()
+    P0 = P.clone()
+    opt = full_opt(d=d, compute_loss_on_training=False)
+    obj = backend.CuALS()
+    obj.init(opt)
+    obj.bind_factors(P, Q)
+    obj.bind_csr(0, indptr, cols, vals)
+    obj.precompute_device(0)
+    obj.update_device(0, 0, U)
+    torch.cuda.synchronize()
+    assert torch.isfinite(P).all()
+    sample = torch.randint(0, U, (300,), generator=torch.Generator().manual_seed(1)).numpy()
+    hind = indptr.cpu().numpy()
+    beg = np.concatenate([[0], hind[:-1]])
+    sub_keys = np.concatenate([cols[beg[u]:hind[u]].cpu().numpy() for u in sample]).astype(np.int32)
+    sub_ind = np.cumsum([hind[u] - beg[u] for u in sample]).astype(np.int64)
+    subP = P0[torch.from_numpy(sample)].cpu().numpy().copy()
+    Qh = Q.cpu().numpy()
+    o = oracle.OracleALS()
+    o.init(opt)
+    o.initialize_model(subP, Qh)
+    o.precompute(0)
+    o.partial_update(0, len(sample), sub_ind, sub_keys, np.ones(len(sub_keys), np.float32), 0)
+    got = P[torch.from_numpy(sample)].cpu().numpy()
+    assert rel_err(got, subP) < FACTOR_TOL
