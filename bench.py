@@ -184,22 +184,15 @@ def cpu_run(sample, opt, cores):
 
 
 def size_cpu_sample(wl, Ph, Qh, opt, cores, target_s):
-    """Pick row fractions so one CPU step lasts about target_s seconds (probe with a tiny slice first)."""
-    probe = cpu_sample_inputs(wl, Ph, Qh, 2e-4, 2e-4)
-    t, nn = cpu_run(probe, opt, cores)
-    # Gram precompute is a fixed cost per step; estimate it separately
-    import oracle
-    o = oracle.OracleALS()
-    o.init(dict(opt, num_workers=cores))
-    o.initialize_model(probe["P"], probe["Q"])
-    t0 = time.perf_counter()
-    o.precompute(0)
-    o.precompute(1)
-    tg = time.perf_counter() - t0
-    rate = nn / max(t - tg, 1e-3)  # nnz/s of the solves
-    want = max(target_s - tg, 1.0) * rate
-    frac = min(0.05, max(2e-4, want / (2.0 * wl["nnz"])))
-    return frac, probe
+    """Grow the row fraction until one CPU step lasts about target_s seconds (bounded sample)."""
+    frac = 2e-4
+    for _ in range(4):
+        sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
+        t, nn = cpu_run(sample, opt, cores)
+        if t >= 0.4 * target_s or frac >= 0.05:
+            break
+        frac = min(0.05, frac * max(2.0, min(20.0, 0.8 * target_s / max(t, 1e-3))))
+    return frac, sample
 
 
 def main():

@@ -40,8 +40,7 @@ struct bfl_als {
     DevBuf<float> gram_part;  // partials of the two-stage Gram
     DevBuf<float> yui;        // generic ialspp scratch
     DevBuf<double> d_loss;    // 2 doubles
-    DevBuf<int32_t> bins;     // row lists of the tuned path
-    DevBuf<int32_t> bin_counts;
+    FastCache fast_cache;     // row-length bins of the tuned path, keyed by (indptr, row range)
     cudaStream_t stream = nullptr;
     int num_sms = 148;
 };
@@ -139,10 +138,18 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     a.reg = axis == 0 ? h->reg_u : h->reg_i;
     a.eps = h->eps;
     a.tol = h->cg_tolerance;
-    const int64_t nrows = row_end - row_begin;
+    int64_t nrows = row_end - row_begin;
 
     if (h->kernel_mode == 0 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
-        return fast_als_launch(a, h->optimizer_code, h->num_sms, h->bins, h->bin_counts, st);
+        const int32_t* left = nullptr;
+        int64_t nleft = 0;
+        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft);
+        if (rc != BFL_OK || nleft == 0) return rc;
+        // rows longer than the tuned kernels accept go through the generic kernel
+        a.row_list = left;
+        a.row_begin = 0;
+        a.row_end = nleft;
+        nrows = nleft;
     }
 
     if (h->optimizer_code == 0 || h->optimizer_code == 1) {
@@ -223,6 +230,7 @@ int bfl_als_set_placeholder(bfl_als_t* h, const int64_t* lindptr, const int64_t*
     BFL_CUDA(cudaMemcpyAsync(h->own_indptr[1].p, rindptr, sizeof(int64_t) * h->Q_rows, cudaMemcpyHostToDevice, h->stream));
     h->d_indptr[0] = h->own_indptr[0].p;
     h->d_indptr[1] = h->own_indptr[1].p;
+    h->fast_cache.clear();
     if (batch_size) {
         if (BFL_OK != h->stage_keys.reserve(batch_size)) return BFL_ERR_CUDA;
         if (BFL_OK != h->stage_vals.reserve(batch_size)) return BFL_ERR_CUDA;
@@ -261,6 +269,7 @@ int bfl_als_partial_update(bfl_als_t* h, int32_t start_x, int32_t next_x, const 
         if (BFL_OK != h->own_indptr[axis].reserve((size_t)rows)) return BFL_ERR_CUDA;
         BFL_CUDA(cudaMemcpyAsync(h->own_indptr[axis].p, indptr, sizeof(int64_t) * rows, cudaMemcpyHostToDevice, h->stream));
         h->d_indptr[axis] = h->own_indptr[axis].p;
+        h->fast_cache.clear();
     }
     const int64_t beg = start_x == 0 ? 0 : indptr[start_x - 1];
     const int64_t end = indptr[next_x - 1];
@@ -308,6 +317,7 @@ int bfl_als_bind_csr_device(bfl_als_t* h, int axis, const int64_t* d_indptr, con
     if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before binding a CSR");
     if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
     if (!d_indptr || (nnz > 0 && (!d_keys || !d_vals)) || rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad CSR arguments");
+    h->fast_cache.clear();
     h->d_indptr[axis] = d_indptr;
     h->d_keys[axis] = d_keys;
     h->d_vals[axis] = d_vals;

@@ -1,12 +1,539 @@
-// Tuned ALS kernels (team-per-row, TMA-staged gathers).  Placeholder until the first GPU
-// validation of the generic path; see DESIGN.md.
+// Tuned iALS++ row-solve kernel for sm_100a (the d >= 128 path, lib/algo_impl/als/als.cc:211-358, and any
+// d % 32 == 0 with block_size 32).
+//
+// Work decomposition
+//   * rows are binned by length; a TEAM of W warps (W = 1..16) owns one row at a time, a CTA of 16 warps
+//     holds 16/W teams, the grid is persistent (one CTA per SM) and strides over the class's row list;
+//   * inside a warp the lane id splits as lane = a + 8*b: `a` (0..7) selects an nnz inside a tile of 32
+//     gathered rows (slots a, a+8, a+16, a+24), `b` (0..3) selects 8 of the 32 columns of the current
+//     column block.  A lane therefore holds a 4 x 8 register patch of the tile and every per-nnz operation
+//     of the block solve (q.p dot, axpy into the block vector) is pure register FMA work:
+//        - a dot product over the block's 32 columns finishes with 2 shuffles (over b),
+//        - a tile's contribution to a 32-vector finishes with a 7-shuffle transposed reduction (over a)
+//          that leaves column `lane` in lane `lane`;
+//   * the gathered opposite-factor segments (128 B per nnz and block) are read with two 128-bit loads per
+//     slot (one full 32 B sector per lane) straight into registers and stay there for the whole block
+//     (b, 3 CG steps, Yui update) when the row fits the team (n <= 32*W*K); longer rows re-gather per pass
+//     (L2 hits);
+//   * the dense terms x.G[:,blk] and A p are expressed as extra "pseudo-nnz" tiles whose rows come from the
+//     Gram matrix held in shared memory, distributed over the team's warps;
+//   * per-row state (x, Yui, alpha*v, keys) lives in shared memory; the CG vector algebra is executed
+//     redundantly by every warp of the team from the same reduced partials (bit-identical, so all warps
+//     take the same early-exit decisions) with one named barrier per reduction.
 #pragma once
+#include <algorithm>
+#include <map>
+
 #include "als_generic.cuh"
 #include "bfl_common.cuh"
 
 namespace bfl {
-inline bool fast_als_applicable(int /*optimizer_code*/, int /*d*/, int /*vdim*/, int /*block_size*/) { return false; }
-inline int fast_als_launch(const AlsArgs&, int, int, DevBuf<int32_t>&, DevBuf<int32_t>&, cudaStream_t) {
-    BFL_FAIL(BFL_ERR_STATE, "tuned ALS kernels not built");
+
+constexpr int FAST_WARPS = 16;
+constexpr int FAST_THREADS = FAST_WARPS * 32;
+constexpr int FAST_NCLASS = 8;
+constexpr int FAST_NR_CAP = 6144;  // longest row the non-resident class accepts (smem for Yui/w/keys)
+
+// class -> (W, K, resident, max nnz)
+struct FastClass { int W, K, res, cap; };
+__host__ __device__ inline FastClass fast_class(int c) {
+    switch (c) {
+        case 0: return {1, 1, 1, 32};
+        case 1: return {1, 2, 1, 64};
+        case 2: return {2, 2, 1, 128};
+        case 3: return {4, 2, 1, 256};
+        case 4: return {8, 2, 1, 512};
+        case 5: return {16, 2, 1, 1024};
+        case 6: return {16, 1, 0, FAST_NR_CAP};
+        default: return {0, 0, 0, 0x7fffffff};  // class 7: too long for the tuned kernels -> generic kernel
+    }
 }
+__host__ __device__ inline int fast_class_of(int64_t n) {
+    if (n <= 32) return 0;
+    if (n <= 64) return 1;
+    if (n <= 128) return 2;
+    if (n <= 256) return 3;
+    if (n <= 512) return 4;
+    if (n <= 1024) return 5;
+    if (n <= FAST_NR_CAP) return 6;
+    return 7;
+}
+
+// ---- binning ------------------------------------------------------------------------------
+__global__ void fast_count_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t row_end,
+                                  unsigned int* __restrict__ counts) {
+    __shared__ unsigned int c[FAST_NCLASS];
+    if (threadIdx.x < FAST_NCLASS) c[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t r = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_end;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = indptr[r] - (r == 0 ? 0 : indptr[r - 1]);
+        if (n > 0) atomicAdd(&c[fast_class_of(n)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < FAST_NCLASS && c[threadIdx.x]) atomicAdd(counts + threadIdx.x, c[threadIdx.x]);
+}
+
+__global__ void fast_fill_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t row_end,
+                                 unsigned int* __restrict__ cursors, int32_t* __restrict__ lists) {
+    for (int64_t r = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_end;
+         r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = indptr[r] - (r == 0 ? 0 : indptr[r - 1]);
+        if (n > 0) {
+            const unsigned int pos = atomicAdd(cursors + fast_class_of(n), 1u);
+            lists[pos] = (int32_t)r;
+        }
+    }
+}
+
+// ---- device helpers -------------------------------------------------------------------------
+template <int W>
+__device__ __forceinline__ void team_sync(int team) {
+    if (W == 1) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(32 * W) : "memory");
+    }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// sum of the 8 a-lanes' acc[k] for column b*8+k, delivered as column `lane` in lane `lane`
+__device__ __forceinline__ float transposed_reduce8(const float (&acc)[8], int la) {
+    float v4[4], v2[2];
+    const bool h4 = la & 4, h2 = la & 2, h1 = la & 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float send = h4 ? acc[k] : acc[k + 4];
+        const float keep = h4 ? acc[k + 4] : acc[k];
+        v4[k] = keep + __shfl_xor_sync(FULL, send, 4);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float send = h2 ? v4[k] : v4[k + 2];
+        const float keep = h2 ? v4[k + 2] : v4[k];
+        v2[k] = keep + __shfl_xor_sync(FULL, send, 2);
+    }
+    const float send = h1 ? v2[0] : v2[1];
+    const float keep = h1 ? v2[1] : v2[0];
+    return keep + __shfl_xor_sync(FULL, send, 1);
+}
+
+__device__ __forceinline__ float dot8(const float (&q)[8], const float (&v)[8]) {
+    float s = q[0] * v[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s = fmaf(q[k], v[k], s);
+    return s;
+}
+// finish a block dot over the 4 b-lanes (lane bits 3,4)
+__device__ __forceinline__ float sum_over_b(float s) {
+    s += __shfl_xor_sync(FULL, s, 8);
+    s += __shfl_xor_sync(FULL, s, 16);
+    return s;
+}
+
+__device__ __forceinline__ void load8(float (&dst)[8], const float* p) {
+    const float4 v0 = lds4(p), v1 = lds4(p + 4);
+    dst[0] = v0.x; dst[1] = v0.y; dst[2] = v0.z; dst[3] = v0.w;
+    dst[4] = v1.x; dst[5] = v1.y; dst[6] = v1.z; dst[7] = v1.w;
+}
+
+// gather the 4 x 8 register patch of tile t, column block B
+__device__ __forceinline__ void gather_patch(float (&q)[4][8], const float* __restrict__ Y, int ld,
+                                             const int32_t* ks, int t, int n, int col0, int la) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int slot = t * 32 + la + 8 * i;
+        if (slot < n) {
+            const float* p = Y + (int64_t)ks[slot] * ld + col0;
+            const float4 v0 = ldg4(p), v1 = ldg4(p + 4);
+            q[i][0] = v0.x; q[i][1] = v0.y; q[i][2] = v0.z; q[i][3] = v0.w;
+            q[i][4] = v1.x; q[i][5] = v1.y; q[i][6] = v1.z; q[i][7] = v1.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[i][k] = 0.f;
+        }
+    }
+}
+
+// dynamic smem: Gs[D*(D+4)] | per team: xs[D] red[2*W*32] pw[W*32] yui[cap] wv[cap] ks[cap]
+__host__ __device__ inline size_t fast_team_floats(int D, int W, int cap) { return (size_t)D + 96 * W + 3 * (size_t)cap; }
+__host__ __device__ inline size_t fast_smem_bytes(int D, int W, int cap) {
+    return sizeof(float) * ((size_t)D * (D + 4) + (FAST_WARPS / W) * fast_team_floats(D, W, cap));
+}
+
+template <int W, int K, bool RES>
+__global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArgs a, int cap) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int TEAMS = FAST_WARPS / W;
+    const int D = a.D, ld = a.ld, GP = D + 4, NB = D >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int team = warp / W, wt = warp % W;
+    const int la = lane & 7, lb = lane >> 3;
+    float* Gs = smem;
+    float* tb = Gs + (size_t)D * GP + (size_t)team * fast_team_floats(D, W, cap);
+    float* xs = tb;
+    float* red = xs + D;            // [2][W][32]
+    float* pw = red + 64 * W + wt * 32;  // this warp's replicated-vector scratch [32]
+    float* yui = red + 96 * W;
+    float* wv = yui + cap;
+    int32_t* ks = reinterpret_cast<int32_t*>(wv + cap);
+
+    for (int e = tid * 4; e < D * D; e += FAST_THREADS * 4) {
+        const float4 g = ldg4(a.G + e);
+        const int r = e / D, c = e - r * D;
+        *reinterpret_cast<float4*>(Gs + r * GP + c) = g;
+    }
+    __syncthreads();
+
+    double l_nume = 0.0, l_deno = 0.0;
+    int par = 0;
+    const float tol = a.tol;
+
+    for (int64_t ri = a.row_begin + (int64_t)blockIdx.x * TEAMS + team; ri < a.row_end;
+         ri += (int64_t)gridDim.x * TEAMS) {
+        const int64_t row = a.row_list[ri];
+        const int64_t beg = row == 0 ? 0 : a.indptr[row - 1];
+        const int n = (int)(a.indptr[row] - beg);
+        const int ntiles = (n + 31) >> 5;
+        float* xrow = a.X + row * ld;
+        team_sync<W>(team);  // the previous row's readers are done with the team's smem
+        for (int c = wt * 32 + lane; c < n; c += 32 * W) {
+            ks[c] = a.keys[beg - a.shift + c];
+            wv[c] = a.vals[beg - a.shift + c] * a.alpha;
+        }
+        for (int j = wt * 32 + lane; j < D; j += 32 * W) xs[j] = xrow[j];
+        team_sync<W>(team);
+
+        // ---- Yui = x . q_c over all D columns (als.cc:256-266), loss pieces with the pre-update row ----
+        for (int t = wt; t < ntiles; t += W) {
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int B = 0; B < NB; ++B) {
+                float xc[8], q[4][8];
+                load8(xc, xs + B * 32 + lb * 8);
+                gather_patch(q, a.Y, ld, ks, t, n, B * 32 + lb * 8, la);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[i] += dot8(q[i], xc);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float dot = sum_over_b(part[i]);
+                const int slot = t * 32 + la + 8 * i;
+                if (lb == 0 && slot < n) {
+                    yui[slot] = dot;
+                    if (a.compute_loss && a.axis == 1) {  // als.cc:310-315
+                        const float av = wv[slot];
+                        l_nume += -(double)(dot * dot) + (double)((dot - 1.f) * (dot - 1.f)) * (1.0 + (double)av);
+                        l_deno += (double)av;
+                    }
+                }
+            }
+        }
+        if (a.compute_loss) {
+            // reg * kappa * |x|^2 (als.cc:319-321) and, item side, x G x (als.cc:298-301); team-strided over j
+            float xx = 0.f, xgx = 0.f;
+            for (int j = wt * 32 + lane; j < D; j += 32 * W) {
+                const float xj = xs[j];
+                xx += xj * xj;
+                if (a.axis == 1) {
+                    float s = 0.f;
+                    for (int k = 0; k < D; ++k) s = fmaf(xs[k], Gs[k * GP + j], s);
+                    xgx += xj * s;
+                }
+            }
+            xx = warp_sum(xx);
+            xgx = warp_sum(xgx);
+            if (lane == 0) {
+                l_nume += (double)((a.adaptive_reg ? (float)n : 1.0f) * a.reg * xx);
+                if (a.axis == 1) {
+                    l_nume += (double)xgx;
+                    if (wt == 0) l_deno += (double)a.Y_rows;
+                }
+            }
+        }
+        team_sync<W>(team);
+
+        // ---- column blocks (als.cc:268-352) ----
+        for (int B = 0; B < NB; ++B) {
+            const int col0 = B * 32 + lb * 8;
+            float q[K][4][8];
+            if (RES) {
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) {
+                    const int t = wt + kk * W;
+                    if (t < ntiles) gather_patch(q[kk], a.Y, ld, ks, t, n, col0, la);
+                }
+            }
+            float acc[8];
+            // b = x G[:,blk] + reg x_blk + sum (Yui - 1) v a q_blk   (als.cc:296,303-308)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+            if (RES) {
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) {
+                    const int t = wt + kk * W;
+                    if (t < ntiles) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int slot = t * 32 + la + 8 * i;
+                            const float cf = slot < n ? (yui[slot] - 1.0f) * wv[slot] : 0.f;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[kk][i][k], acc[k]);
+                        }
+                    }
+                }
+            } else {
+                for (int t = wt; t < ntiles; t += W) {
+                    gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int slot = t * 32 + la + 8 * i;
+                        const float cf = slot < n ? (yui[slot] - 1.0f) * wv[slot] : 0.f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[0][i][k], acc[k]);
+                    }
+                }
+            }
+            for (int pt = 0; pt < NB; ++pt) {  // pseudo tiles: rows of G[:, blk], coefficient x_i
+                if ((W - 1 - (pt % W)) != wt) continue;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int i = pt * 32 + la + 8 * m;
+                    const float cf = xs[i];
+                    float g8[8];
+                    load8(g8, Gs + i * GP + col0);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, g8[k], acc[k]);
+                }
+            }
+            red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
+            team_sync<W>(team);
+            float g = a.reg * xs[B * 32 + lane];
+#pragma unroll
+            for (int w = 0; w < W; ++w) g += red[par * W * 32 + w * 32 + lane];
+            par ^= 1;
+
+            // ---- 3 CG steps on (A + sum v a q q^T) delta = g, A = G[blk,blk] + reg I (als.cc:278,324-345) ----
+            float xv = 0.f, r = g, p = g;
+            double rsold = (double)warp_sum(r * r);
+            if (rsold > (double)tol) {
+                for (int step = 0; step < 3; ++step) {
+                    __syncwarp();
+                    pw[lane] = p;
+                    __syncwarp();
+                    float pc[8];
+                    load8(pc, pw + lb * 8);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+                    if (RES) {
+#pragma unroll
+                        for (int kk = 0; kk < K; ++kk) {
+                            const int t = wt + kk * W;
+                            if (t < ntiles) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const int slot = t * 32 + la + 8 * i;
+                                    const float dot = sum_over_b(dot8(q[kk][i], pc));
+                                    const float cf = slot < n ? wv[slot] * dot : 0.f;
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[kk][i][k], acc[k]);
+                                }
+                            }
+                        }
+                    } else {
+                        for (int t = wt; t < ntiles; t += W) {
+                            gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int slot = t * 32 + la + 8 * i;
+                                const float dot = sum_over_b(dot8(q[0][i], pc));
+                                const float cf = slot < n ? wv[slot] * dot : 0.f;
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[0][i][k], acc[k]);
+                            }
+                        }
+                    }
+                    if (wt == W - 1) {  // pseudo tile: rows of G[blk, blk], coefficient p_i
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            const int i = la + 8 * m;
+                            const float cf = pw[i];
+                            float g8[8];
+                            load8(g8, Gs + (B * 32 + i) * GP + col0);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, g8[k], acc[k]);
+                        }
+                    }
+                    red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
+                    team_sync<W>(team);
+                    float Ap = a.reg * p;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) Ap += red[par * W * 32 + w * 32 + lane];
+                    par ^= 1;
+                    const float pAp = warp_sum(p * Ap);
+                    const float step_size = (float)(rsold / (double)pAp);  // als.cc:337, no eps
+                    xv = fmaf(step_size, p, xv);
+                    r = fmaf(-step_size, Ap, r);
+                    const double rsnew = (double)warp_sum(r * r);
+                    if (rsnew < (double)tol) break;  // als.cc:341
+                    p = fmaf((float)(rsnew / rsold), p, r);
+                    rsold = rsnew;
+                }
+            }
+            // ---- x_blk -= delta ; Yui -= q_blk . delta  (als.cc:346-350) ----
+            __syncwarp();
+            pw[lane] = xv;
+            __syncwarp();
+            float xc[8];
+            load8(xc, pw + lb * 8);
+            if (RES) {
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) {
+                    const int t = wt + kk * W;
+                    if (t < ntiles) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int slot = t * 32 + la + 8 * i;
+                            const float dot = sum_over_b(dot8(q[kk][i], xc));
+                            if (lb == 0 && slot < n) yui[slot] -= dot;
+                        }
+                    }
+                }
+            } else {
+                for (int t = wt; t < ntiles; t += W) {
+                    gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int slot = t * 32 + la + 8 * i;
+                        const float dot = sum_over_b(dot8(q[0][i], xc));
+                        if (lb == 0 && slot < n) yui[slot] -= dot;
+                    }
+                }
+            }
+            if (wt == 0) xs[B * 32 + lane] -= xv;
+            team_sync<W>(team);
+        }
+        // NaN/Inf guard (cf. als.cu:116-120), then write the row back
+        bool bad = false;
+        for (int j = lane; j < D; j += 32) bad |= !isfinite(xs[j]);
+        bad = __any_sync(FULL, bad);
+        for (int j = wt * 32 + lane; j < D; j += 32 * W) xrow[j] = bad ? 0.f : xs[j];
+    }
+    if (a.loss && a.compute_loss) {
+        l_nume = warp_sum_d(l_nume);
+        l_deno = warp_sum_d(l_deno);
+        if (lane == 0 && (l_nume != 0.0 || l_deno != 0.0)) {
+            atomicAdd(a.loss, l_nume);
+            atomicAdd(a.loss + 1, l_deno);
+        }
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+struct FastBins {
+    DevBuf<int32_t> lists;           // all classes back to back
+    DevBuf<unsigned int> counters;   // [0..7] counts, [8..15] cursors
+    unsigned int count[FAST_NCLASS] = {0};
+    unsigned int offset[FAST_NCLASS + 1] = {0};
+};
+struct FastBinKey {
+    const void* indptr; int64_t b, e;
+    bool operator<(const FastBinKey& o) const {
+        if (indptr != o.indptr) return indptr < o.indptr;
+        if (b != o.b) return b < o.b;
+        return e < o.e;
+    }
+};
+struct FastCache {
+    std::map<FastBinKey, FastBins*> bins;
+    void clear() {
+        for (auto& kv : bins) delete kv.second;
+        bins.clear();
+    }
+    ~FastCache() { clear(); }
+};
+
+inline bool fast_als_applicable(int optimizer_code, int d, int vdim, int block_size) {
+    return optimizer_code == 8 && d % 32 == 0 && d <= 128 && vdim == d && block_size == 32;
+}
+
+template <int W, int K, bool RES>
+int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
+    const size_t smem = fast_smem_bytes(a.D, W, cap);
+    static bool configured = false;
+    if (!configured) {
+        BFL_CUDA(cudaFuncSetAttribute(als_ialspp_team_kernel<W, K, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      200 * 1024));
+        configured = true;
+    }
+    if (smem > 200 * 1024) BFL_FAIL(BFL_ERR_STATE, "tuned ALS kernel: shared memory budget exceeded");
+    const int64_t nrows = a.row_end - a.row_begin;
+    constexpr int TEAMS = FAST_WARPS / W;
+    const int grid = (int)std::min<int64_t>((nrows + TEAMS - 1) / TEAMS, (int64_t)num_sms);
+    als_ialspp_team_kernel<W, K, RES><<<grid, FAST_THREADS, smem, st>>>(a, cap);
+    BFL_LAUNCHED();
+    return BFL_OK;
+}
+
+// bins rows [row_begin,row_end) of a.indptr by length (cached per (indptr,row range)) and launches one
+// kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`
+inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cudaStream_t st,
+                           const int32_t** leftover_rows, int64_t* leftover_count) {
+    *leftover_rows = nullptr;
+    *leftover_count = 0;
+    const int64_t nrows = a0.row_end - a0.row_begin;
+    FastBinKey key{a0.indptr, a0.row_begin, a0.row_end};
+    FastBins* fb = nullptr;
+    auto it = cache.bins.find(key);
+    if (it == cache.bins.end()) {
+        if (cache.bins.size() >= 256) cache.clear();
+        fb = new FastBins();
+        if (BFL_OK != fb->lists.reserve((size_t)nrows) || BFL_OK != fb->counters.reserve(2 * FAST_NCLASS)) {
+            delete fb;
+            return BFL_ERR_CUDA;
+        }
+        BFL_CUDA(cudaMemsetAsync(fb->counters.p, 0, 2 * FAST_NCLASS * sizeof(unsigned int), st));
+        const int grid = (int)std::min<int64_t>((nrows + 255) / 256, (int64_t)num_sms * 8);
+        fast_count_kernel<<<grid, 256, 0, st>>>(a0.indptr, a0.row_begin, a0.row_end, fb->counters.p);
+        BFL_LAUNCHED();
+        BFL_CUDA(cudaMemcpyAsync(fb->count, fb->counters.p, FAST_NCLASS * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        BFL_CUDA(cudaStreamSynchronize(st));
+        fb->offset[0] = 0;
+        for (int c = 0; c < FAST_NCLASS; ++c) fb->offset[c + 1] = fb->offset[c] + fb->count[c];
+        BFL_CUDA(cudaMemcpyAsync(fb->counters.p + FAST_NCLASS, fb->offset, FAST_NCLASS * sizeof(unsigned int),
+                                 cudaMemcpyHostToDevice, st));
+        fast_fill_kernel<<<grid, 256, 0, st>>>(a0.indptr, a0.row_begin, a0.row_end, fb->counters.p + FAST_NCLASS,
+                                               fb->lists.p);
+        BFL_LAUNCHED();
+        cache.bins[key] = fb;
+    } else {
+        fb = it->second;
+    }
+    for (int c = 0; c < FAST_NCLASS - 1; ++c) {
+        if (!fb->count[c]) continue;
+        AlsArgs a = a0;
+        a.row_list = fb->lists.p;
+        a.row_begin = fb->offset[c];
+        a.row_end = fb->offset[c + 1];
+        const FastClass fc = fast_class(c);
+        int rc = BFL_OK;
+        switch (c) {
+            case 0: rc = fast_launch_class<1, 1, true>(a, fc.cap, num_sms, st); break;
+            case 1: rc = fast_launch_class<1, 2, true>(a, fc.cap, num_sms, st); break;
+            case 2: rc = fast_launch_class<2, 2, true>(a, fc.cap, num_sms, st); break;
+            case 3: rc = fast_launch_class<4, 2, true>(a, fc.cap, num_sms, st); break;
+            case 4: rc = fast_launch_class<8, 2, true>(a, fc.cap, num_sms, st); break;
+            case 5: rc = fast_launch_class<16, 2, true>(a, fc.cap, num_sms, st); break;
+            case 6: rc = fast_launch_class<16, 1, false>(a, fc.cap, num_sms, st); break;
+        }
+        if (rc != BFL_OK) return rc;
+    }
+    if (fb->count[FAST_NCLASS - 1]) {
+        *leftover_rows = fb->lists.p + fb->offset[FAST_NCLASS - 1];
+        *leftover_count = fb->count[FAST_NCLASS - 1];
+    }
+    return BFL_OK;
+}
+
 }  // namespace bfl

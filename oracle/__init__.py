@@ -173,7 +173,11 @@ class OracleSGD(object):
         self.epoch = 0
         self.processed = 0.0
         self.total = float(num_total_samples) * self.o.num_iters
-        self.lr = float(self.o.lr)
+        # lr / min_lr / beta1 are doubles in the reference (opt_["lr"].number_value(), algo.cc:267-268,394-396)
+        self.lr0 = float(self.opt.get("lr", 0.05))
+        self.min_lr = float(self.opt.get("min_lr", 0.0001))
+        self.beta1 = float(self.opt.get("beta1", 0.9))
+        self.lr = self.lr0
         z = np.zeros_like
         if self.o.optimizer != 0:  # initialize_adam_optimizer (algo.cc:221-254)
             self.gP, self.gQ, self.gQb = z(P), z(Q), z(Qb)
@@ -217,7 +221,7 @@ class OracleSGD(object):
         if next_x - start_x == 0:
             return
         # job.alpha = lr_ at job creation (algo.cc:351,359); decay by processed fraction (algo.cc:284-287)
-        self.lr = lib().orc_lr_decay(float(self.o.lr), float(self.o.min_lr), self.processed, self.total)
+        self.lr = lib().orc_lr_decay(self.lr0, self.min_lr, self.processed, self.total)
         beg = 0 if start_x == 0 else int(indptr[start_x - 1])
         nnz = int(indptr[next_x - 1]) - beg
         if self.warp:
@@ -242,13 +246,13 @@ class OracleSGD(object):
                                         (self.Q, self.gQ, self.mQ, self.vQ, self.cQ, o.reg_i)]:
                 lib().orc_sgd_apply(o.optimizer, _f32(th), _f32(g), _f32(m), _f32(v), _i32(c),
                                     C.c_int64(th.shape[0]), int(th.shape[1]), C.c_double(reg),
-                                    C.c_double(o.lr), C.c_double(o.beta1), int(self.iters),
+                                    C.c_double(self.lr0), C.c_double(self.beta1), int(self.iters),
                                     int(o.per_coordinate_normalize), int(o.num_workers))
             if o.use_bias and not self.warp:
                 # bias grads are normalised by the item counters too (algo.cc:411-413)
                 lib().orc_sgd_apply(o.optimizer, _f32(self.Qb), _f32(self.gQb), _f32(self.mQb), _f32(self.vQb),
                                     _i32(self.cQ), C.c_int64(self.Qb.shape[0]), 1, C.c_double(o.reg_b),
-                                    C.c_double(o.lr), C.c_double(o.beta1), int(self.iters),
+                                    C.c_double(self.lr0), C.c_double(self.beta1), int(self.iters),
                                     int(o.per_coordinate_normalize), int(o.num_workers))
             if o.per_coordinate_normalize:
                 self.cP[:] = 0

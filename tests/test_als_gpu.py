@@ -109,8 +109,10 @@ def test_parity_vs_oracle(cuda_lib, d, optimizer, kw):
 
 def test_c1_config_training_trajectory(cuda_lib):
     """BASELINE configs[0]: ALS d=32 on 10k x 5k, 200k nnz, default options, from the reference's own
-    initialisation abs(N(0, 1/d^2)) (als.py:85-86): three full iterations, GPU and oracle advanced side by
-    side from their own states; factors and RMSE must agree at every iteration."""
+    initialisation abs(N(0, 1/d^2)) (als.py:85-86), three full iterations.
+    (1) every half-epoch started from the oracle's state matches the oracle to 1e-3 (the parity bar);
+    (2) the GPU's own trajectory (never re-synchronised) stays within 5e-3 of the oracle's and reports the
+        same RMSE (als.py:171) -- 3-step CG does not contract rounding differences, so they add up."""
     U, I, nnz, d = 10000, 5000, 200000, 32
     indptr, keys, vals, _ = make_csr(U, I, nnz, seed=1234)
     cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
@@ -119,14 +121,54 @@ def test_c1_config_training_trajectory(cuda_lib):
     Qg = init_factors(I, d, d, 8)
     Po, Qo = Pg.copy(), Qg.copy()
     for it in range(3):
-        Pg, n1, d1 = gpu_half(opt, Pg, Qg, indptr, keys, vals, 0)
-        Qg, n2, d2 = gpu_half(opt, Pg, Qg, cind, ckeys, cvals, 1)
+        Ps, _, _ = gpu_half(opt, Po, Qo, indptr, keys, vals, 0)         # (1) from the oracle's state
+        Pg, n1, d1 = gpu_half(opt, Pg, Qg, indptr, keys, vals, 0)       # (2) own trajectory
         Po, m1, e1 = oracle_half(opt, Po, Qo, indptr, keys, vals, 0)
+        assert rel_err(Ps, Po) < FACTOR_TOL, it
+        Qs, _, _ = gpu_half(opt, Po, Qo, cind, ckeys, cvals, 1)
+        Qg, n2, d2 = gpu_half(opt, Pg, Qg, cind, ckeys, cvals, 1)
         Qo, m2, e2 = oracle_half(opt, Po, Qo, cind, ckeys, cvals, 1)
-        assert rel_err(Pg, Po) < FACTOR_TOL and rel_err(Qg, Qo) < FACTOR_TOL, it
+        assert rel_err(Qs, Qo) < FACTOR_TOL, it
+        assert rel_err(Pg, Po) < 5e-3 and rel_err(Qg, Qo) < 5e-3, it
         rmse_g = ((n1 + n2) / (d1 + d2 + 1e-10)) ** 0.5     # als.py:171
         rmse_o = ((m1 + m2) / (e1 + e2 + 1e-10)) ** 0.5
         assert abs(rmse_g - rmse_o) < 1e-4 * rmse_o
+
+
+@pytest.mark.parametrize("d", [128, 64, 32])
+def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
+    """The tuned iALS++ kernel bins rows by length (<=32, 64, 128, 256, 512, 1024 register-resident; <=6144
+    re-gathering; longer rows fall back to the generic kernel).  One input that hits every class, checked
+    against the oracle and against the generic kernel (_b200_kernel_mode=1)."""
+    rng = np.random.default_rng(d)
+    lengths = np.concatenate([rng.integers(1, 33, 300), rng.integers(33, 65, 200), rng.integers(65, 129, 150),
+                              rng.integers(129, 257, 80), rng.integers(257, 513, 40), rng.integers(513, 1025, 20),
+                              rng.integers(1025, 6145, 6), [6145, 7000, 1024, 1025, 32, 33, 0, 0, 1]])
+    rng.shuffle(lengths)
+    U, I = len(lengths), 9000
+    keys = np.concatenate([np.sort(rng.choice(I, size=n, replace=False)) for n in lengths]).astype(np.int32)
+    indptr = np.cumsum(lengths).astype(np.int64)
+    vals = rng.integers(1, 4, len(keys)).astype(np.float32)
+    opt = full_opt(d=d, optimizer="ialspp", block_size=32)
+    P = init_factors(U, d, d, 1, scale=0.05, signed=True)
+    Q = init_factors(I, d, d, 2, scale=0.05, signed=True)
+    for axis_opt in (dict(), dict(adaptive_reg=True)):
+        o = dict(opt, **axis_opt)
+        X0, n0, dn0 = oracle_half(o, P, Q, indptr, keys, vals, 0)
+        Xf, nf, dnf = gpu_half(o, P, Q, indptr, keys, vals, 0)
+        Xg, ng, dng = gpu_half(dict(o, _b200_kernel_mode=1), P, Q, indptr, keys, vals, 0)
+        assert rel_err(Xf, X0) < FACTOR_TOL and rel_err(Xg, X0) < FACTOR_TOL
+        assert rel_err(Xf, Xg) < FACTOR_TOL
+        check_loss(nf, dnf, n0, dn0)
+    # item side (loss has the extra x G x and observed terms): reuse the same CSR as a colwise matrix
+    X0, n0, dn0 = oracle_half(opt, Q[:U].copy(), np.vstack([P, np.zeros((I - U, d), np.float32)])[:I], indptr, keys, vals, 1) \
+        if False else (None, None, None)
+    Pi = init_factors(I, d, d, 3, scale=0.05, signed=True)      # "users" are now the opposite side
+    Qi = init_factors(U, d, d, 4, scale=0.05, signed=True)      # rows being updated (axis 1)
+    X0, n0, dn0 = oracle_half(opt, Pi, Qi, indptr, keys, vals, 1)
+    Xf, nf, dnf = gpu_half(opt, Pi, Qi, indptr, keys, vals, 1)
+    assert rel_err(Xf, X0) < FACTOR_TOL
+    check_loss(nf, dnf, n0, dn0)
 
 
 def test_chunked_equals_whole_and_placeholder(cuda_lib):
