@@ -161,8 +161,6 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
         assert rel_err(Xf, Xg) < FACTOR_TOL
         check_loss(nf, dnf, n0, dn0)
     # item side (loss has the extra x G x and observed terms): reuse the same CSR as a colwise matrix
-    X0, n0, dn0 = oracle_half(opt, Q[:U].copy(), np.vstack([P, np.zeros((I - U, d), np.float32)])[:I], indptr, keys, vals, 1) \
-        if False else (None, None, None)
     Pi = init_factors(I, d, d, 3, scale=0.05, signed=True)      # "users" are now the opposite side
     Qi = init_factors(U, d, d, 4, scale=0.05, signed=True)      # rows being updated (axis 1)
     X0, n0, dn0 = oracle_half(opt, Pi, Qi, indptr, keys, vals, 1)
