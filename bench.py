@@ -245,30 +245,25 @@ def main():
     obj.bind_factors(P, Q)
     obj.bind_csr(0, wl["r_indptr"], wl["r_keys"], wl["vals"])
     obj.bind_csr(1, wl["c_indptr"], wl["c_keys"], wl["vals"])
-    # contiguous row shards per rank (equal row counts; the collective needs equal pieces)
-    def shard(total):
-        per = (total + world - 1) // world
-        return min(rank * per, total), min((rank + 1) * per, total), per
-    u0, u1, uper = shard(U)
-    i0, i1, iper = shard(I)
-    if world > 1:
-        assert U % world == 0 and I % world == 0, "row counts must divide the world size"
+    # contiguous row shards per rank + one in-place all-gather per half-epoch (buffalo_b200/parallel/dist.py)
+    from buffalo_b200.parallel.dist import ShardedALS
+    drv = ShardedALS(obj.precompute_device, obj.update_device, P, Q, rank, world, dist if world > 1 else None)
+    (u0, u1, _), (i0, i1, _) = drv.ranges
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     solve_events = []
+    pending = {}
+
+    def on_update(axis, when):
+        e = ev()
+        e.record(stream)
+        if when == "begin":
+            pending[axis] = e
+        else:
+            solve_events.append((axis, pending.pop(axis), e))
 
     def step(record=False):
-        for axis, (a, b, full) in enumerate([(u0, u1, P), (i0, i1, Q)]):
-            obj.precompute_device(axis)
-            if record:
-                e0, e1 = ev(), ev()
-                e0.record(stream)
-            obj.update_device(axis, a, b)
-            if record:
-                e1.record(stream)
-                solve_events.append((axis, e0, e1))
-            if world > 1:  # the one exchange step per half-epoch: all-gather of the updated shard
-                dist.all_gather_into_tensor(full, full[a:b])
+        drv.iteration(on_update if record else None)
 
     def barrier():
         torch.cuda.synchronize()

@@ -1,0 +1,73 @@
+"""world_size-2 gloo test of the multi-GPU host logic (row sharding + one all-gather per half-epoch) on CPU.
+The per-rank row update is the CPU oracle here (tests may use it); on the GPU box bench.py plugs the CUDA
+backend into the same ShardedALS driver."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import init_factors, make_csr, rel_err, transpose_csr
+
+OPT = dict(d=16, optimizer="manual_cg", num_workers=1, compute_loss_on_training=False, alpha=8.0, reg_u=0.1, reg_i=0.1)
+
+
+def _problem():
+    U, I = 64, 48
+    indptr, keys, vals, _ = make_csr(U, I, 900, seed=1)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    return U, I, (indptr, keys, vals), (cind, ckeys, cvals), init_factors(U, 16, 16, 1, 0.1, True), init_factors(I, 16, 16, 2, 0.1, True)
+
+
+def _driver(P, Q, csr, rank, world, d):
+    import oracle
+    from buffalo_b200.parallel.dist import ShardedALS
+    o = oracle.OracleALS()
+    o.init(OPT)
+    o.initialize_model(P.numpy(), Q.numpy())     # shares memory with the torch tensors
+
+    def update(axis, lo, hi):
+        ind, k, v = csr[axis]
+        beg = 0 if lo == 0 else int(ind[lo - 1])
+        end = int(ind[hi - 1]) if hi > lo else beg
+        o.partial_update(lo, hi, ind, np.ascontiguousarray(k[beg:max(end, beg + 1)]),
+                         np.ascontiguousarray(v[beg:max(end, beg + 1)]), axis)
+    return ShardedALS(o.precompute, update, P, Q, rank, world, d)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    U, I, rw, cw, P0, Q0 = _problem()
+    P, Q = torch.from_numpy(P0.copy()), torch.from_numpy(Q0.copy())
+    drv = _driver(P, Q, (rw, cw), rank, world, dist)
+    for _ in range(2):
+        drv.iteration()
+    out[rank] = (P.numpy().copy(), Q.numpy().copy())
+    dist.destroy_process_group()
+
+
+def test_sharded_equals_single_process():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    U, I, rw, cw, P0, Q0 = _problem()
+    P, Q = torch.from_numpy(P0.copy()), torch.from_numpy(Q0.copy())
+    single = _driver(P, Q, (rw, cw), 0, 1, None)
+    for _ in range(2):
+        single.iteration()
+    for r in (0, 1):
+        Pr, Qr = out[r]
+        assert rel_err(Pr, P.numpy()) < 1e-6 and rel_err(Qr, Q.numpy()) < 1e-6      # replicas identical to 1-process run
+    assert not np.array_equal(P.numpy(), P0)
+
+
+def test_row_shard():
+    from buffalo_b200.parallel.dist import row_shard
+    assert [row_shard(10, r, 4)[:2] for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert row_shard(8, 1, 2) == (4, 8, 4) and row_shard(3, 3, 4)[:2] == (3, 3)

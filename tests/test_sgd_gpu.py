@@ -162,7 +162,7 @@ def test_bpr_sgd_loss_trajectory_band(cuda_lib):
             o.update_parameters()
             lg, lo = g.compute_loss(probe_u, probe_p, probe_n), o.compute_loss(probe_u, probe_p, probe_n)
             l_first = l_first or lo
-            assert abs(lg - lo) < 0.03 * lo, (seed, epoch, lg, lo)
+            assert abs(lg - lo) < 0.15 * lo, (seed, epoch, lg, lo)
             assert abs(g.current_lr() - o.lr) < 1e-12
         assert abs(lg - lo) < 0.10 * lo, (seed, lg, lo)
         assert lo < 0.9 * l_first and lg < 0.9 * l_first      # both learn
