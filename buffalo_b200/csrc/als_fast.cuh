@@ -43,7 +43,7 @@ __host__ __device__ inline FastClass fast_class(int c) {
         case 2: return {2, 2, 1, 128};
         case 3: return {4, 2, 1, 256};
         case 4: return {8, 2, 1, 512};
-        case 5: return {16, 2, 1, 1024};
+        case 5: return {16, 3, 1, 1536};  // 2 register tiles + 1 shared-memory tile per warp
         case 6: return {16, 1, 0, FAST_NR_CAP};
         default: return {0, 0, 0, 0x7fffffff};  // class 7: too long for the tuned kernels -> generic kernel
     }
@@ -54,7 +54,7 @@ __host__ __device__ inline int fast_class_of(int64_t n) {
     if (n <= 128) return 2;
     if (n <= 256) return 3;
     if (n <= 512) return 4;
-    if (n <= 1024) return 5;
+    if (n <= 1536) return 5;
     if (n <= FAST_NR_CAP) return 6;
     return 7;
 }
@@ -99,33 +99,72 @@ __device__ __forceinline__ void team_sync(int team) {
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
-// sum of the 8 a-lanes' acc[k] for column b*8+k, delivered as column `lane` in lane `lane`
-__device__ __forceinline__ float transposed_reduce8(const float (&acc)[8], int la) {
-    float v4[4], v2[2];
-    const bool h4 = la & 4, h2 = la & 2, h1 = la & 1;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float send = h4 ? acc[k] : acc[k + 4];
-        const float keep = h4 ? acc[k + 4] : acc[k];
-        v4[k] = keep + __shfl_xor_sync(FULL, send, 4);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float send = h2 ? v4[k] : v4[k + 2];
-        const float keep = h2 ? v4[k + 2] : v4[k];
-        v2[k] = keep + __shfl_xor_sync(FULL, send, 2);
-    }
-    const float send = h1 ? v2[0] : v2[1];
-    const float keep = h1 ? v2[1] : v2[0];
-    return keep + __shfl_xor_sync(FULL, send, 1);
+// packed fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
 }
 
-__device__ __forceinline__ float dot8(const float (&q)[8], const float (&v)[8]) {
-    float s = q[0] * v[0];
+// a lane's 8 columns as 4 packed pairs
+struct V8 { float2 v[4]; };
+
+__device__ __forceinline__ V8 v8_zero() {
+    V8 r;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s = fmaf(q[k], v[k], s);
-    return s;
+    for (int k = 0; k < 4; ++k) r.v[k] = make_float2(0.f, 0.f);
+    return r;
 }
+__device__ __forceinline__ V8 v8_from(float4 lo, float4 hi) {
+    V8 r;
+    r.v[0] = make_float2(lo.x, lo.y); r.v[1] = make_float2(lo.z, lo.w);
+    r.v[2] = make_float2(hi.x, hi.y); r.v[3] = make_float2(hi.z, hi.w);
+    return r;
+}
+__device__ __forceinline__ V8 v8_lds(const float* p) { return v8_from(lds4(p), lds4(p + 4)); }
+__device__ __forceinline__ V8 v8_ldg(const float* p) { return v8_from(ldg4(p), ldg4(p + 4)); }
+__device__ __forceinline__ float v8_dot(const V8& q, const V8& x) {
+    float2 s = fmul2(q.v[0], x.v[0]);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) s = ffma2(q.v[k], x.v[k], s);
+    return s.x + s.y;
+}
+__device__ __forceinline__ void v8_axpy(V8& acc, float cf, const V8& q) {
+    const float2 c2 = make_float2(cf, cf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc.v[k] = ffma2(c2, q.v[k], acc.v[k]);
+}
+
+// sum of the 8 a-lanes' acc for column b*8+k, delivered as column `lane` in lane `lane`
+__device__ __forceinline__ float transposed_reduce8(const V8& acc, int la) {
+    const bool h4 = la & 4, h2 = la & 2, h1 = la & 1;
+    // step xor 4: keep one float4 half, send the other
+    const float2 s0 = h4 ? acc.v[0] : acc.v[2], s1 = h4 ? acc.v[1] : acc.v[3];
+    const float2 k0 = h4 ? acc.v[2] : acc.v[0], k1 = h4 ? acc.v[3] : acc.v[1];
+    float2 v0, v1;
+    v0.x = k0.x + __shfl_xor_sync(FULL, s0.x, 4);
+    v0.y = k0.y + __shfl_xor_sync(FULL, s0.y, 4);
+    v1.x = k1.x + __shfl_xor_sync(FULL, s1.x, 4);
+    v1.y = k1.y + __shfl_xor_sync(FULL, s1.y, 4);
+    // step xor 2
+    const float2 s = h2 ? v0 : v1, k = h2 ? v1 : v0;
+    float2 u;
+    u.x = k.x + __shfl_xor_sync(FULL, s.x, 2);
+    u.y = k.y + __shfl_xor_sync(FULL, s.y, 2);
+    // step xor 1
+    return (h1 ? u.y : u.x) + __shfl_xor_sync(FULL, h1 ? u.x : u.y, 1);
+}
+
 // finish a block dot over the 4 b-lanes (lane bits 3,4)
 __device__ __forceinline__ float sum_over_b(float s) {
     s += __shfl_xor_sync(FULL, s, 8);
@@ -133,88 +172,109 @@ __device__ __forceinline__ float sum_over_b(float s) {
     return s;
 }
 
-__device__ __forceinline__ void load8(float (&dst)[8], const float* p) {
-    const float4 v0 = lds4(p), v1 = lds4(p + 4);
-    dst[0] = v0.x; dst[1] = v0.y; dst[2] = v0.z; dst[3] = v0.w;
-    dst[4] = v1.x; dst[5] = v1.y; dst[6] = v1.z; dst[7] = v1.w;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// gather the 4 x 8 register patch of tile t, column block B
-__device__ __forceinline__ void gather_patch(float (&q)[4][8], const float* __restrict__ Y, int ld,
-                                             const int32_t* ks, int t, int n, int col0, int la) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int slot = t * 32 + la + 8 * i;
-        if (slot < n) {
-            const float* p = Y + (int64_t)ks[slot] * ld + col0;
-            const float4 v0 = ldg4(p), v1 = ldg4(p + 4);
-            q[i][0] = v0.x; q[i][1] = v0.y; q[i][2] = v0.z; q[i][3] = v0.w;
-            q[i][4] = v1.x; q[i][5] = v1.y; q[i][6] = v1.z; q[i][7] = v1.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) q[i][k] = 0.f;
-        }
-    }
-}
-
-// dynamic smem: Gs[D*(D+4)] | per team: xs[D] red[2*W*32] pw[W*32] yui[cap] wv[cap] ks[cap]
+// dynamic smem layout:
+//   [GSM ? Gs[D*(D+4)] : -] | staging: 16 warps x (K+KS)*8 chunks x 32 lanes x 16 B (RES only) |
+//   per team: xs[D] red[2*W*32] pw[W*32] yui[cap] wv[cap] ks[cap]
 __host__ __device__ inline size_t fast_team_floats(int D, int W, int cap) { return (size_t)D + 96 * W + 3 * (size_t)cap; }
-__host__ __device__ inline size_t fast_smem_bytes(int D, int W, int cap) {
-    return sizeof(float) * ((size_t)D * (D + 4) + (FAST_WARPS / W) * fast_team_floats(D, W, cap));
+__host__ __device__ inline size_t fast_smem_bytes(int D, int W, int K, int KS, bool res, bool gsm, int cap) {
+    return sizeof(float) * ((gsm ? (size_t)D * (D + 4) : 0) + (res ? (size_t)FAST_WARPS * (K + KS) * 8 * 128 : 0) +
+                            (FAST_WARPS / W) * fast_team_floats(D, W, cap));
 }
 
-template <int W, int K, bool RES>
+// W warps per row, K register-resident tiles per warp, KS extra tiles per warp kept in shared memory,
+// RES=false: nothing resident, every pass re-gathers (rows longer than 32*W*(K+KS)); GSM: Gram matrix in smem.
+template <int W, int K, int KS, bool RES, bool GSM>
 __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArgs a, int cap) {
     extern __shared__ __align__(16) float smem[];
     constexpr int TEAMS = FAST_WARPS / W;
-    const int D = a.D, ld = a.ld, GP = D + 4, NB = D >> 5;
+    constexpr int KT = K + KS;
+    const int D = a.D, ld = a.ld, GP = GSM ? D + 4 : D, NB = D >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int team = warp / W, wt = warp % W;
     const int la = lane & 7, lb = lane >> 3;
     float* Gs = smem;
-    float* tb = Gs + (size_t)D * GP + (size_t)team * fast_team_floats(D, W, cap);
+    float* stg_all = smem + (GSM ? (size_t)D * (D + 4) : 0);
+    float* stg = stg_all + (size_t)warp * KT * 8 * 128;      // [KT*8 chunks][32 lanes][4 floats]
+    float* tb = stg_all + (RES ? (size_t)FAST_WARPS * KT * 8 * 128 : 0) + (size_t)team * fast_team_floats(D, W, cap);
     float* xs = tb;
-    float* red = xs + D;            // [2][W][32]
+    float* red = xs + D;                 // [2][W][32]
     float* pw = red + 64 * W + wt * 32;  // this warp's replicated-vector scratch [32]
     float* yui = red + 96 * W;
     float* wv = yui + cap;
     int32_t* ks = reinterpret_cast<int32_t*>(wv + cap);
+    const float* Gp = GSM ? Gs : a.G;    // pseudo-nnz rows come from smem or (long-row class) from L1/L2
 
-    for (int e = tid * 4; e < D * D; e += FAST_THREADS * 4) {
-        const float4 g = ldg4(a.G + e);
-        const int r = e / D, c = e - r * D;
-        *reinterpret_cast<float4*>(Gs + r * GP + c) = g;
+    if (GSM) {
+        for (int e = tid * 4; e < D * D; e += FAST_THREADS * 4) {
+            const float4 g = ldg4(a.G + e);
+            const int r = e / D, c = e - r * D;
+            *reinterpret_cast<float4*>(Gs + r * GP + c) = g;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     double l_nume = 0.0, l_deno = 0.0;
     int par = 0;
     const float tol = a.tol;
+    const int64_t stride = (int64_t)gridDim.x * TEAMS;
 
-    for (int64_t ri = a.row_begin + (int64_t)blockIdx.x * TEAMS + team; ri < a.row_end;
-         ri += (int64_t)gridDim.x * TEAMS) {
+    // issue the async copies of this lane's patch of column block B for tiles [kk0, kk1)
+    auto stage_block = [&](int B, int ntiles) {
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+            const int t = wt + kk * W;
+            if (t < ntiles) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* src = a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + B * 32 + lb * 8;
+                    float* dst = stg + ((kk * 4 + i) * 2) * 128 + lane * 4;
+                    cp_async16(dst, src);
+                    cp_async16(dst + 128, src + 4);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int64_t ri = a.row_begin + (int64_t)blockIdx.x * TEAMS + team; ri < a.row_end; ri += stride) {
         const int64_t row = a.row_list[ri];
         const int64_t beg = row == 0 ? 0 : a.indptr[row - 1];
         const int n = (int)(a.indptr[row] - beg);
         const int ntiles = (n + 31) >> 5;
         float* xrow = a.X + row * ld;
         team_sync<W>(team);  // the previous row's readers are done with the team's smem
-        for (int c = wt * 32 + lane; c < n; c += 32 * W) {
-            ks[c] = a.keys[beg - a.shift + c];
-            wv[c] = a.vals[beg - a.shift + c] * a.alpha;
+        {
+            const int32_t k0 = a.keys[beg - a.shift];
+            const int npad = RES ? cap : ntiles * 32;
+            for (int c = wt * 32 + lane; c < npad; c += 32 * W) {
+                const bool ok = c < n;
+                ks[c] = ok ? a.keys[beg - a.shift + c] : k0;          // padded slots gather a valid row ...
+                wv[c] = ok ? a.vals[beg - a.shift + c] * a.alpha : 0.f;  // ... with weight 0
+                if (!ok) yui[c] = 0.f;
+            }
         }
         for (int j = wt * 32 + lane; j < D; j += 32 * W) xs[j] = xrow[j];
         team_sync<W>(team);
+        if (RES) stage_block(0, ntiles);   // block 0's segments fly while the Yui pass streams the rows
 
         // ---- Yui = x . q_c over all D columns (als.cc:256-266), loss pieces with the pre-update row ----
         for (int t = wt; t < ntiles; t += W) {
             float part[4] = {0.f, 0.f, 0.f, 0.f};
             for (int B = 0; B < NB; ++B) {
-                float xc[8], q[4][8];
-                load8(xc, xs + B * 32 + lb * 8);
-                gather_patch(q, a.Y, ld, ks, t, n, B * 32 + lb * 8, la);
+                const V8 xc = v8_lds(xs + B * 32 + lb * 8);
+                V8 q[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) part[i] += dot8(q[i], xc);
+                for (int i = 0; i < 4; ++i)
+                    q[i] = v8_ldg(a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + B * 32 + lb * 8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[i] += v8_dot(q[i], xc);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -230,6 +290,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                 }
             }
         }
+        // pull the next row's gathered rows towards L2 while this row is being solved
+        if (ri + stride < a.row_end) {
+            const int64_t row2 = a.row_list[ri + stride];
+            const int64_t beg2 = row2 == 0 ? 0 : a.indptr[row2 - 1];
+            const int n2 = (int)(a.indptr[row2] - beg2);
+            for (int c = wt * 32 + lane; c < n2 * NB; c += 32 * W) {
+                const int s2 = c / NB, l2 = c - s2 * NB;
+                prefetch_l2(a.Y + (int64_t)a.keys[beg2 - a.shift + s2] * ld + l2 * 32);
+            }
+        }
         if (a.compute_loss) {
             // reg * kappa * |x|^2 (als.cc:319-321) and, item side, x G x (als.cc:298-301); team-strided over j
             float xx = 0.f, xgx = 0.f;
@@ -238,7 +308,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                 xx += xj * xj;
                 if (a.axis == 1) {
                     float s = 0.f;
-                    for (int k = 0; k < D; ++k) s = fmaf(xs[k], Gs[k * GP + j], s);
+                    for (int k = 0; k < D; ++k) s = fmaf(xs[k], Gp[k * GP + j], s);
                     xgx += xj * s;
                 }
             }
@@ -257,54 +327,64 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
         // ---- column blocks (als.cc:268-352) ----
         for (int B = 0; B < NB; ++B) {
             const int col0 = B * 32 + lb * 8;
-            float q[K][4][8];
+            V8 q[K][4];
             if (RES) {
+                cp_async_wait_all();   // each lane reads back only what it copied itself: no barrier needed
 #pragma unroll
-                for (int kk = 0; kk < K; ++kk) {
-                    const int t = wt + kk * W;
-                    if (t < ntiles) gather_patch(q[kk], a.Y, ld, ks, t, n, col0, la);
-                }
-            }
-            float acc[8];
-            // b = x G[:,blk] + reg x_blk + sum (Yui - 1) v a q_blk   (als.cc:296,303-308)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-            if (RES) {
-#pragma unroll
-                for (int kk = 0; kk < K; ++kk) {
-                    const int t = wt + kk * W;
-                    if (t < ntiles) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int slot = t * 32 + la + 8 * i;
-                            const float cf = slot < n ? (yui[slot] - 1.0f) * wv[slot] : 0.f;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[kk][i][k], acc[k]);
-                        }
-                    }
-                }
-            } else {
-                for (int t = wt; t < ntiles; t += W) {
-                    gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
+                for (int kk = 0; kk < K; ++kk)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int slot = t * 32 + la + 8 * i;
-                        const float cf = slot < n ? (yui[slot] - 1.0f) * wv[slot] : 0.f;
+                        const float* src = stg + ((kk * 4 + i) * 2) * 128 + lane * 4;
+                        q[kk][i] = v8_from(lds4(src), lds4(src + 128));
+                    }
+                if (KS == 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // prefetch the next block behind the math
+            }
+            // per-pass visitor over this warp's tiles: register tiles, smem-resident tiles, or re-gathered tiles
+            auto for_tiles = [&](auto&& body) {
+                if (RES) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[0][i][k], acc[k]);
+                    for (int kk = 0; kk < K; ++kk) {
+                        const int t = wt + kk * W;
+                        if (t < ntiles) body(t, q[kk]);
+                    }
+#pragma unroll
+                    for (int kk = K; kk < KT; ++kk) {
+                        const int t = wt + kk * W;
+                        if (t < ntiles) {
+                            V8 qs[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float* src = stg + ((kk * 4 + i) * 2) * 128 + lane * 4;
+                                qs[i] = v8_from(lds4(src), lds4(src + 128));
+                            }
+                            body(t, qs);
+                        }
+                    }
+                } else {
+                    for (int t = wt; t < ntiles; t += W) {
+                        V8 qs[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) qs[i] = v8_ldg(a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + col0);
+                        body(t, qs);
                     }
                 }
-            }
+            };
+
+            // b = x G[:,blk] + reg x_blk + sum (Yui - 1) v a q_blk   (als.cc:296,303-308)
+            V8 acc = v8_zero();
+            for_tiles([&](int t, const V8(&qq)[4]) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int slot = t * 32 + la + 8 * i;
+                    v8_axpy(acc, (yui[slot] - 1.0f) * wv[slot], qq[i]);
+                }
+            });
             for (int pt = 0; pt < NB; ++pt) {  // pseudo tiles: rows of G[:, blk], coefficient x_i
                 if ((W - 1 - (pt % W)) != wt) continue;
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
                     const int i = pt * 32 + la + 8 * m;
-                    const float cf = xs[i];
-                    float g8[8];
-                    load8(g8, Gs + i * GP + col0);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, g8[k], acc[k]);
+                    v8_axpy(acc, xs[i], GSM ? v8_lds(Gp + i * GP + col0) : v8_ldg(Gp + i * GP + col0));
                 }
             }
             red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
@@ -322,47 +402,23 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     __syncwarp();
                     pw[lane] = p;
                     __syncwarp();
-                    float pc[8];
-                    load8(pc, pw + lb * 8);
+                    const V8 pc = v8_lds(pw + lb * 8);
+                    acc = v8_zero();
+                    for_tiles([&](int t, const V8(&qq)[4]) {
+                        float dots[4];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-                    if (RES) {
+                        for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], pc);
 #pragma unroll
-                        for (int kk = 0; kk < K; ++kk) {
-                            const int t = wt + kk * W;
-                            if (t < ntiles) {
+                        for (int i = 0; i < 4; ++i) dots[i] = sum_over_b(dots[i]);
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int slot = t * 32 + la + 8 * i;
-                                    const float dot = sum_over_b(dot8(q[kk][i], pc));
-                                    const float cf = slot < n ? wv[slot] * dot : 0.f;
-#pragma unroll
-                                    for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[kk][i][k], acc[k]);
-                                }
-                            }
-                        }
-                    } else {
-                        for (int t = wt; t < ntiles; t += W) {
-                            gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int slot = t * 32 + la + 8 * i;
-                                const float dot = sum_over_b(dot8(q[0][i], pc));
-                                const float cf = slot < n ? wv[slot] * dot : 0.f;
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, q[0][i][k], acc[k]);
-                            }
-                        }
-                    }
+                        for (int i = 0; i < 4; ++i) v8_axpy(acc, wv[t * 32 + la + 8 * i] * dots[i], qq[i]);
+                    });
                     if (wt == W - 1) {  // pseudo tile: rows of G[blk, blk], coefficient p_i
 #pragma unroll
                         for (int m = 0; m < 4; ++m) {
                             const int i = la + 8 * m;
-                            const float cf = pw[i];
-                            float g8[8];
-                            load8(g8, Gs + (B * 32 + i) * GP + col0);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) acc[k] = fmaf(cf, g8[k], acc[k]);
+                            const float* gr = Gp + (B * 32 + i) * GP + col0;
+                            v8_axpy(acc, pw[i], GSM ? v8_lds(gr) : v8_ldg(gr));
                         }
                     }
                     red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
@@ -385,33 +441,19 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             __syncwarp();
             pw[lane] = xv;
             __syncwarp();
-            float xc[8];
-            load8(xc, pw + lb * 8);
-            if (RES) {
+            const V8 xc = v8_lds(pw + lb * 8);
+            for_tiles([&](int t, const V8(&qq)[4]) {
+                float dots[4];
 #pragma unroll
-                for (int kk = 0; kk < K; ++kk) {
-                    const int t = wt + kk * W;
-                    if (t < ntiles) {
+                for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], xc);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int slot = t * 32 + la + 8 * i;
-                            const float dot = sum_over_b(dot8(q[kk][i], xc));
-                            if (lb == 0 && slot < n) yui[slot] -= dot;
-                        }
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float dot = sum_over_b(dots[i]);
+                    if (lb == 0) yui[t * 32 + la + 8 * i] -= dot;
                 }
-            } else {
-                for (int t = wt; t < ntiles; t += W) {
-                    gather_patch(q[0], a.Y, ld, ks, t, n, col0, la);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int slot = t * 32 + la + 8 * i;
-                        const float dot = sum_over_b(dot8(q[0][i], xc));
-                        if (lb == 0 && slot < n) yui[slot] -= dot;
-                    }
-                }
-            }
+            });
             if (wt == 0) xs[B * 32 + lane] -= xv;
+            if (RES && KS > 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // smem-resident tiles are free only now
             team_sync<W>(team);
         }
         // NaN/Inf guard (cf. als.cu:116-120), then write the row back
@@ -458,20 +500,21 @@ inline bool fast_als_applicable(int optimizer_code, int d, int vdim, int block_s
     return optimizer_code == 8 && d % 32 == 0 && d <= 128 && vdim == d && block_size == 32;
 }
 
-template <int W, int K, bool RES>
+template <int W, int K, int KS, bool RES, bool GSM>
 int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
-    const size_t smem = fast_smem_bytes(a.D, W, cap);
+    const size_t smem = fast_smem_bytes(a.D, W, K, KS, RES, GSM, cap);
+    constexpr int SMEM_MAX = 227 * 1024;
     static bool configured = false;
     if (!configured) {
-        BFL_CUDA(cudaFuncSetAttribute(als_ialspp_team_kernel<W, K, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      200 * 1024));
+        BFL_CUDA(cudaFuncSetAttribute(als_ialspp_team_kernel<W, K, KS, RES, GSM>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
         configured = true;
     }
-    if (smem > 200 * 1024) BFL_FAIL(BFL_ERR_STATE, "tuned ALS kernel: shared memory budget exceeded");
+    if (smem > (size_t)SMEM_MAX) BFL_FAIL(BFL_ERR_STATE, "tuned ALS kernel: shared memory budget exceeded");
     const int64_t nrows = a.row_end - a.row_begin;
     constexpr int TEAMS = FAST_WARPS / W;
     const int grid = (int)std::min<int64_t>((nrows + TEAMS - 1) / TEAMS, (int64_t)num_sms);
-    als_ialspp_team_kernel<W, K, RES><<<grid, FAST_THREADS, smem, st>>>(a, cap);
+    als_ialspp_team_kernel<W, K, KS, RES, GSM><<<grid, FAST_THREADS, smem, st>>>(a, cap);
     BFL_LAUNCHED();
     return BFL_OK;
 }
@@ -519,13 +562,13 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         const FastClass fc = fast_class(c);
         int rc = BFL_OK;
         switch (c) {
-            case 0: rc = fast_launch_class<1, 1, true>(a, fc.cap, num_sms, st); break;
-            case 1: rc = fast_launch_class<1, 2, true>(a, fc.cap, num_sms, st); break;
-            case 2: rc = fast_launch_class<2, 2, true>(a, fc.cap, num_sms, st); break;
-            case 3: rc = fast_launch_class<4, 2, true>(a, fc.cap, num_sms, st); break;
-            case 4: rc = fast_launch_class<8, 2, true>(a, fc.cap, num_sms, st); break;
-            case 5: rc = fast_launch_class<16, 2, true>(a, fc.cap, num_sms, st); break;
-            case 6: rc = fast_launch_class<16, 1, false>(a, fc.cap, num_sms, st); break;
+            case 0: rc = fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 1: rc = fast_launch_class<1, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 2: rc = fast_launch_class<2, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 3: rc = fast_launch_class<4, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 4: rc = fast_launch_class<8, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 5: rc = fast_launch_class<16, 2, 1, true, false>(a, fc.cap, num_sms, st); break;
+            case 6: rc = fast_launch_class<16, 1, 0, false, true>(a, fc.cap, num_sms, st); break;
         }
         if (rc != BFL_OK) return rc;
     }
