@@ -29,8 +29,10 @@ struct bfl_als {
     // CSR per axis
     DevBuf<int64_t> own_indptr[2];
     const int64_t* d_indptr[2] = {nullptr, nullptr};
-    DevBuf<int32_t> stage_keys;
+    DevBuf<int32_t> stage_keys;   // two halves: double-buffered sub-chunks of the host-pointer path
     DevBuf<float> stage_vals;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
     const int32_t* d_keys[2] = {nullptr, nullptr};  // resident CSR (device path)
     const float* d_vals[2] = {nullptr, nullptr};
     int64_t csr_rows[2] = {0, 0}, csr_nnz[2] = {0, 0};
@@ -75,7 +77,15 @@ int als_apply_options(bfl_als* h, const JsonOpt& j) {
     int dev = 0;
     BFL_CUDA(cudaGetDevice(&dev));
     BFL_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
-    if (!h->stream) BFL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (!h->stream) {
+        BFL_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        BFL_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        BFL_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            BFL_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            BFL_CUDA(cudaEventCreateWithFlags(&h->ev_comp[i], cudaEventDisableTiming));
+        }
+    }
     if (BFL_OK != h->G.reserve((size_t)h->d * h->d)) return BFL_ERR_CUDA;
     if (BFL_OK != h->d_loss.reserve(2)) return BFL_ERR_CUDA;
     h->opt_set = true;
@@ -182,6 +192,12 @@ bfl_als_t* bfl_als_create(void) { return new (std::nothrow) bfl_als(); }
 void bfl_als_destroy(bfl_als_t* h) {
     if (!h) return;
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_comp[i]) cudaEventDestroy(h->ev_comp[i]);
+    }
     delete h;
 }
 
@@ -274,24 +290,63 @@ int bfl_als_partial_update(bfl_als_t* h, int32_t start_x, int32_t next_x, const 
     const int64_t beg = start_x == 0 ? 0 : indptr[start_x - 1];
     const int64_t end = indptr[next_x - 1];
     const int64_t n = end - beg;
-    if (n > 0) {
-        if (BFL_OK != h->stage_keys.reserve((size_t)n)) return BFL_ERR_CUDA;
-        if (BFL_OK != h->stage_vals.reserve((size_t)n)) return BFL_ERR_CUDA;
-        BFL_CUDA(cudaMemcpyAsync(h->stage_keys.p, keys, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
-        BFL_CUDA(cudaMemcpyAsync(h->stage_vals.p, vals, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    // The chunk is cut into row-aligned sub-chunks of <= SUB entries and software-pipelined over three streams:
+    // H2D of sub-chunk k+1 (keys, vals) | row solves of sub-chunk k | D2H of the rows updated by sub-chunk k-1.
+    // With pinned host buffers the PCIe traffic of the reference protocol (als.cu:361-364,403) overlaps the math.
+    const int64_t SUB = 16ll << 20;
+    int64_t maxsub = 0;
+    std::vector<int64_t> cut;  // row boundaries
+    cut.push_back(start_x);
+    {
+        int64_t r = start_x;
+        while (r < next_x) {
+            const int64_t b0 = r == 0 ? 0 : indptr[r - 1];
+            // largest r2 > r with indptr[r2-1] - b0 <= SUB (at least one row)
+            int64_t lo = r + 1, hi = next_x;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi + 1) >> 1;
+                if (indptr[mid - 1] - b0 <= SUB) lo = mid; else hi = mid - 1;
+            }
+            maxsub = std::max(maxsub, indptr[lo - 1] - b0);
+            cut.push_back(lo);
+            r = lo;
+        }
     }
+    const int nsub = (int)cut.size() - 1;
+    if (BFL_OK != h->stage_keys.reserve((size_t)std::max<int64_t>(2 * maxsub, 2))) return BFL_ERR_CUDA;
+    if (BFL_OK != h->stage_vals.reserve((size_t)std::max<int64_t>(2 * maxsub, 2))) return BFL_ERR_CUDA;
     BFL_CUDA(cudaMemsetAsync(h->d_loss.p, 0, 2 * sizeof(double), h->stream));
-    int rc = solve_rows(h, axis, start_x, next_x, h->stage_keys.p, h->stage_vals.p, beg, n, h->d_loss.p, h->stream);
-    if (rc != BFL_OK) return rc;
-    double hl[2] = {0.0, 0.0};
-    BFL_CUDA(cudaMemcpyAsync(hl, h->d_loss.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    // copy the updated rows back into the caller's matrix (als.cu:321-336,403)
     float* hostF = axis == 0 ? h->hostP : h->hostQ;
     float* devF = axis == 0 ? h->dP : h->dQ;
-    const size_t off = (size_t)start_x * h->vdim;
-    BFL_CUDA(cudaMemcpyAsync(hostF + off, devF + off, sizeof(float) * (size_t)(next_x - start_x) * h->vdim,
-                             cudaMemcpyDeviceToHost, h->stream));
+    (void)n;
+    for (int k = 0; k < nsub; ++k) {
+        const int64_t r0 = cut[k], r1 = cut[k + 1];
+        const int64_t b0 = r0 == 0 ? 0 : indptr[r0 - 1];
+        const int64_t cnt = indptr[r1 - 1] - b0;
+        const int slot = k & 1;
+        int32_t* dk = h->stage_keys.p + (size_t)slot * maxsub;
+        float* dv = h->stage_vals.p + (size_t)slot * maxsub;
+        if (k >= 2) BFL_CUDA(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[slot], 0));  // staging half is free again
+        if (cnt > 0) {
+            BFL_CUDA(cudaMemcpyAsync(dk, keys + (b0 - beg), sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->s_h2d));
+            BFL_CUDA(cudaMemcpyAsync(dv, vals + (b0 - beg), sizeof(float) * cnt, cudaMemcpyHostToDevice, h->s_h2d));
+        }
+        BFL_CUDA(cudaEventRecord(h->ev_h2d[slot], h->s_h2d));
+        BFL_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[slot], 0));
+        int rc = solve_rows(h, axis, r0, r1, dk, dv, b0, cnt, h->d_loss.p, h->stream);
+        if (rc != BFL_OK) return rc;
+        BFL_CUDA(cudaEventRecord(h->ev_comp[slot], h->stream));
+        // copy the rows this sub-chunk updated back into the caller's matrix (als.cu:321-336,403)
+        BFL_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[slot], 0));
+        const size_t off = (size_t)r0 * h->vdim;
+        BFL_CUDA(cudaMemcpyAsync(hostF + off, devF + off, sizeof(float) * (size_t)(r1 - r0) * h->vdim,
+                                 cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    double hl[2] = {0.0, 0.0};
+    BFL_CUDA(cudaMemcpyAsync(hl, h->d_loss.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     BFL_CUDA(cudaStreamSynchronize(h->stream));
+    BFL_CUDA(cudaStreamSynchronize(h->s_d2h));
+    BFL_CUDA(cudaStreamSynchronize(h->s_h2d));
     if (loss_nume) *loss_nume = hl[0];
     if (loss_deno) *loss_deno = hl[1];
     return BFL_OK;

@@ -32,7 +32,7 @@ namespace bfl {
 constexpr int FAST_WARPS = 16;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_NCLASS = 8;
-constexpr int FAST_NR_CAP = 6144;  // longest row the non-resident class accepts (smem for Yui/w/keys)
+constexpr int FAST_NR_CAP = 12288;  // longest row the non-resident class accepts (smem for Yui/w/keys)
 
 // class -> (W, K, resident, max nnz)
 struct FastClass { int W, K, res, cap; };
@@ -181,8 +181,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // dynamic smem layout:
 //   [GSM ? Gs[D*(D+4)] : -] | staging: 16 warps x (K+KS)*8 chunks x 32 lanes x 16 B (RES only) |
-//   per team: xs[D] red[2*W*32] pw[W*32] yui[cap] wv[cap] ks[cap]
-__host__ __device__ inline size_t fast_team_floats(int D, int W, int cap) { return (size_t)D + 96 * W + 3 * (size_t)cap; }
+//   per team: xs[D] red[2*W*32] pw[W*32] racc[3*32] yui[cap] wv[cap] ks[cap]
+__host__ __device__ inline size_t fast_team_floats(int D, int W, int cap) { return (size_t)D + 96 * W + 96 + 3 * (size_t)cap; }
 __host__ __device__ inline size_t fast_smem_bytes(int D, int W, int K, int KS, bool res, bool gsm, int cap) {
     return sizeof(float) * ((gsm ? (size_t)D * (D + 4) : 0) + (res ? (size_t)FAST_WARPS * (K + KS) * 8 * 128 : 0) +
                             (FAST_WARPS / W) * fast_team_floats(D, W, cap));
@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     float* xs = tb;
     float* red = xs + D;                 // [2][W][32]
     float* pw = red + 64 * W + wt * 32;  // this warp's replicated-vector scratch [32]
-    float* yui = red + 96 * W;
+    float* racc = red + 96 * W;          // [3][32] rotating shared-memory accumulators (W >= 4)
+    float* yui = racc + 96;
     float* wv = yui + cap;
     int32_t* ks = reinterpret_cast<int32_t*>(wv + cap);
     const float* Gp = GSM ? Gs : a.G;    // pseudo-nnz rows come from smem or (long-row class) from L1/L2
@@ -223,6 +224,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     double l_nume = 0.0, l_deno = 0.0;
     int par = 0;
     const float tol = a.tol;
+    // Team-wide sum of one 32-vector (lane = column).  W <= 2: partials in smem, summed in warp order
+    // (deterministic).  W >= 4: red.shared.add into one of three rotating accumulators: every warp then reads the
+    // SAME total, so the redundant CG algebra stays bit-identical across the team (summation order, hence the last
+    // bits, may differ between runs).  Rotation: reduction k uses buffer k%3; warp 0 clears buffer (k+1)%3 before
+    // arriving at barrier k -- every warp has finished reading it because it passed barrier k-1.
+    constexpr bool ATOMIC_RED = W >= 4;
+    if (ATOMIC_RED && wt == 0) {
+        racc[lane] = 0.f; racc[32 + lane] = 0.f; racc[64 + lane] = 0.f;
+    }
+    auto team_reduce = [&](float v) -> float {
+        if (W == 1) return v;
+        if (ATOMIC_RED) {
+            const int nxt = par == 2 ? 0 : par + 1;
+            if (wt == 0) racc[nxt * 32 + lane] = 0.f;
+            atomicAdd(racc + par * 32 + lane, v);
+            team_sync<W>(team);
+            const float tot = racc[par * 32 + lane];
+            par = nxt;
+            return tot;
+        } else {
+            red[par * W * 32 + wt * 32 + lane] = v;
+            team_sync<W>(team);
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < W; ++w) tot += red[par * W * 32 + w * 32 + lane];
+            par ^= 1;
+            return tot;
+        }
+    };
     const int64_t stride = (int64_t)gridDim.x * TEAMS;
 
     // issue the async copies of this lane's patch of column block B for tiles [kk0, kk1)
@@ -267,14 +297,26 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
         // ---- Yui = x . q_c over all D columns (als.cc:256-266), loss pieces with the pre-update row ----
         for (int t = wt; t < ntiles; t += W) {
             float part[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int B = 0; B < NB; ++B) {
-                const V8 xc = v8_lds(xs + B * 32 + lb * 8);
-                V8 q[4];
+            const float* rowp[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    q[i] = v8_ldg(a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + B * 32 + lb * 8);
+            for (int i = 0; i < 4; ++i) rowp[i] = a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + lb * 8;
+            for (int B = 0; B < NB; B += 2) {   // two column blocks (64 B per slot) in flight per step
+                V8 q0[4], q1[4];
+                const bool two = B + 1 < NB;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) part[i] += v8_dot(q[i], xc);
+                for (int i = 0; i < 4; ++i) q0[i] = v8_ldg(rowp[i] + B * 32);
+                if (two) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) q1[i] = v8_ldg(rowp[i] + B * 32 + 32);
+                }
+                const V8 x0 = v8_lds(xs + B * 32 + lb * 8);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) part[i] += v8_dot(q0[i], x0);
+                if (two) {
+                    const V8 x1 = v8_lds(xs + B * 32 + 32 + lb * 8);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) part[i] += v8_dot(q1[i], x1);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -291,7 +333,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             }
         }
         // pull the next row's gathered rows towards L2 while this row is being solved
-        if (ri + stride < a.row_end) {
+        if (W <= 8 && ri + stride < a.row_end) {   // long rows: the in-flight working set already fills L2
             const int64_t row2 = a.row_list[ri + stride];
             const int64_t beg2 = row2 == 0 ? 0 : a.indptr[row2 - 1];
             const int n2 = (int)(a.indptr[row2] - beg2);
@@ -387,17 +429,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     v8_axpy(acc, xs[i], GSM ? v8_lds(Gp + i * GP + col0) : v8_ldg(Gp + i * GP + col0));
                 }
             }
-            red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
-            team_sync<W>(team);
-            float g = a.reg * xs[B * 32 + lane];
-#pragma unroll
-            for (int w = 0; w < W; ++w) g += red[par * W * 32 + w * 32 + lane];
-            par ^= 1;
+            const float g = team_reduce(transposed_reduce8(acc, la)) + a.reg * xs[B * 32 + lane];
 
             // ---- 3 CG steps on (A + sum v a q q^T) delta = g, A = G[blk,blk] + reg I (als.cc:278,324-345) ----
             float xv = 0.f, r = g, p = g;
-            double rsold = (double)warp_sum(r * r);
-            if (rsold > (double)tol) {
+            float rsold = warp_sum(r * r);
+            if (rsold > tol) {
                 for (int step = 0; step < 3; ++step) {
                     __syncwarp();
                     pw[lane] = p;
@@ -421,19 +458,16 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                             v8_axpy(acc, pw[i], GSM ? v8_lds(gr) : v8_ldg(gr));
                         }
                     }
-                    red[par * W * 32 + wt * 32 + lane] = transposed_reduce8(acc, la);
-                    team_sync<W>(team);
-                    float Ap = a.reg * p;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) Ap += red[par * W * 32 + w * 32 + lane];
-                    par ^= 1;
+                    const float Ap = team_reduce(transposed_reduce8(acc, la)) + a.reg * p;
                     const float pAp = warp_sum(p * Ap);
-                    const float step_size = (float)(rsold / (double)pAp);  // als.cc:337, no eps
+                    // als.cc:337 (no eps): the reference divides a double holding a float by a float and rounds to
+                    // float; an fp32 division of the same two floats gives that quotient (up to double rounding)
+                    const float step_size = __fdiv_rn(rsold, pAp);
                     xv = fmaf(step_size, p, xv);
                     r = fmaf(-step_size, Ap, r);
-                    const double rsnew = (double)warp_sum(r * r);
-                    if (rsnew < (double)tol) break;  // als.cc:341
-                    p = fmaf((float)(rsnew / rsold), p, r);
+                    const float rsnew = warp_sum(r * r);
+                    if (rsnew < tol) break;  // als.cc:341
+                    p = fmaf(__fdiv_rn(rsnew, rsold), p, r);
                     rsold = rsnew;
                 }
             }

@@ -20,7 +20,8 @@ def launches(path):
         v = float(r[iv].replace(",", ""))
         v = v / 1e6 if r[iu] in ("nsecond", "ns") else (v / 1e3 if r[iu] in ("usecond", "us") else v)  # -> ms
         name = r[ik].split("(")[0].replace("void ", "").replace("bfl::", "")
-        name = name if "at::native" not in name and "cub::" not in name and "thrust" not in name else "torch (workload generation)"
+        ours_prefixes = ("als_", "gram_", "fast_", "bpr_", "warp_", "sgd_", "probe_")
+        name = name if name.startswith(ours_prefixes) else "torch (workload generation)"
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += v

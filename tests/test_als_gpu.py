@@ -137,15 +137,16 @@ def test_c1_config_training_trajectory(cuda_lib):
 
 @pytest.mark.parametrize("d", [128, 64, 32])
 def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
-    """The tuned iALS++ kernel bins rows by length (<=32, 64, 128, 256, 512, 1024 register-resident; <=6144
-    re-gathering; longer rows fall back to the generic kernel).  One input that hits every class, checked
-    against the oracle and against the generic kernel (_b200_kernel_mode=1)."""
+    """The tuned iALS++ kernel bins rows by length (<=32, 64, 128, 256, 512 register-resident; <=1536 two register
+    tiles + one shared-memory tile per warp; <=12288 re-gathering; longer rows fall back to the generic kernel).
+    One input that hits every class, checked against the oracle and the generic kernel (_b200_kernel_mode=1)."""
     rng = np.random.default_rng(d)
     lengths = np.concatenate([rng.integers(1, 33, 300), rng.integers(33, 65, 200), rng.integers(65, 129, 150),
                               rng.integers(129, 257, 80), rng.integers(257, 513, 40), rng.integers(513, 1025, 20),
-                              rng.integers(1025, 6145, 6), [6145, 7000, 1024, 1025, 32, 33, 0, 0, 1]])
+                              rng.integers(1025, 1537, 12), rng.integers(1537, 12289, 5),
+                              [12289, 13000, 1536, 1537, 1024, 1025, 512, 513, 32, 33, 0, 0, 1]])
     rng.shuffle(lengths)
-    U, I = len(lengths), 9000
+    U, I = len(lengths), 14000
     keys = np.concatenate([np.sort(rng.choice(I, size=n, replace=False)) for n in lengths]).astype(np.int32)
     indptr = np.cumsum(lengths).astype(np.int64)
     vals = rng.integers(1, 4, len(keys)).astype(np.float32)
