@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     constexpr int TEAMS = FAST_WARPS / W;
     constexpr int KT = K + KS;
     const int D = a.D, ld = a.ld, GP = GSM ? D + 4 : D, NB = D >> 5;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast through lane 0 so the compiler knows the warp index (and everything derived from it: team, row
+    // loop, trip counts) is warp-uniform; otherwise every shuffle below is compiled as a WARPSYNC.COLLECTIVE call
+    const int warp = __shfl_sync(FULL, tid >> 5, 0);
     const int team = warp / W, wt = warp % W;
     const int la = lane & 7, lb = lane >> 3;
     float* Gs = smem;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
             const int t = wt + kk * W;
-            if (t < ntiles) {
+            if (kk < K || t < ntiles) {   // register tiles: always (padded slots gather a valid row, weight 0)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float* src = a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + B * 32 + lb * 8;
@@ -274,11 +277,11 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     };
 
     for (int64_t ri = a.row_begin + (int64_t)blockIdx.x * TEAMS + team; ri < a.row_end; ri += stride) {
-        const int64_t row = a.row_list[ri];
+        const int row = __shfl_sync(FULL, a.row_list[ri], 0);
         const int64_t beg = row == 0 ? 0 : a.indptr[row - 1];
-        const int n = (int)(a.indptr[row] - beg);
+        const int n = __shfl_sync(FULL, (int)(a.indptr[row] - beg), 0);
         const int ntiles = (n + 31) >> 5;
-        float* xrow = a.X + row * ld;
+        float* xrow = a.X + (int64_t)row * ld;
         team_sync<W>(team);  // the previous row's readers are done with the team's smem
         {
             const int32_t k0 = a.keys[beg - a.shift];
@@ -375,10 +378,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             auto for_tiles = [&](auto&& body) {
                 if (RES) {
 #pragma unroll
-                    for (int kk = 0; kk < K; ++kk) {
-                        const int t = wt + kk * W;
-                        if (t < ntiles) body(t, q[kk]);
-                    }
+                    for (int kk = 0; kk < K; ++kk) body(wt + kk * W, q[kk]);   // branch-free: padding has weight 0
 #pragma unroll
                     for (int kk = K; kk < KT; ++kk) {
                         const int t = wt + kk * W;
@@ -422,44 +422,47 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             const float g = team_reduce(transposed_reduce8(acc, la)) + a.reg * xs[B * 32 + lane];
 
             // ---- 3 CG steps on (A + sum v a q q^T) delta = g, A = G[blk,blk] + reg I (als.cc:278,324-345) ----
+            // The reference skips the solve when rsold <= tol and leaves the loop when rsnew < tol (als.cc:329,341).
+            // Here the three steps always run and those conditions only mask the updates: identical results, no
+            // data-dependent branch around the shuffles / team barriers.
             float xv = 0.f, r = g, p = g;
             float rsold = warp_sum(r * r);
-            if (rsold > tol) {
-                for (int step = 0; step < 3; ++step) {
-                    __syncwarp();
-                    pw[lane] = p;
-                    __syncwarp();
-                    const V8 pc = v8_lds(pw + lb * 8);
-                    acc = v8_zero();
-                    for_tiles([&](int t, const V8(&qq)[4]) {
-                        float dots[4];
+            bool act = rsold > tol;
+#pragma unroll 1
+            for (int step = 0; step < 3; ++step) {
+                __syncwarp();
+                pw[lane] = p;
+                __syncwarp();
+                const V8 pc = v8_lds(pw + lb * 8);
+                acc = v8_zero();
+                for_tiles([&](int t, const V8(&qq)[4]) {
+                    float dots[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], pc);
+                    for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], pc);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dots[i] = sum_over_b(dots[i]);
+                    for (int i = 0; i < 4; ++i) dots[i] = sum_over_b(dots[i]);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) v8_axpy(acc, wv[t * 32 + la + 8 * i] * dots[i], qq[i]);
-                    });
-                    if (wt == W - 1) {  // pseudo tile: rows of G[blk, blk], coefficient p_i
+                    for (int i = 0; i < 4; ++i) v8_axpy(acc, wv[t * 32 + la + 8 * i] * dots[i], qq[i]);
+                });
+                if (wt == W - 1) {  // pseudo tile: rows of G[blk, blk], coefficient p_i
 #pragma unroll
-                        for (int m = 0; m < 4; ++m) {
-                            const int i = la + 8 * m;
-                            const float* gr = Gp + (B * 32 + i) * GP + col0;
-                            v8_axpy(acc, pw[i], GSM ? v8_lds(gr) : v8_ldg(gr));
-                        }
+                    for (int m = 0; m < 4; ++m) {
+                        const int i = la + 8 * m;
+                        const float* gr = Gp + (B * 32 + i) * GP + col0;
+                        v8_axpy(acc, pw[i], GSM ? v8_lds(gr) : v8_ldg(gr));
                     }
-                    const float Ap = team_reduce(transposed_reduce8(acc, la)) + a.reg * p;
-                    const float pAp = warp_sum(p * Ap);
-                    // als.cc:337 (no eps): the reference divides a double holding a float by a float and rounds to
-                    // float; an fp32 division of the same two floats gives that quotient (up to double rounding)
-                    const float step_size = __fdiv_rn(rsold, pAp);
-                    xv = fmaf(step_size, p, xv);
-                    r = fmaf(-step_size, Ap, r);
-                    const float rsnew = warp_sum(r * r);
-                    if (rsnew < tol) break;  // als.cc:341
-                    p = fmaf(__fdiv_rn(rsnew, rsold), p, r);
-                    rsold = rsnew;
                 }
+                const float Ap = team_reduce(transposed_reduce8(acc, la)) + a.reg * p;
+                const float pAp = warp_sum(p * Ap);
+                // als.cc:337 (no eps): the reference divides a double holding a float by a float and rounds to
+                // float; an fp32 division of the same two floats gives that quotient (up to double rounding)
+                const float step_size = act ? __fdiv_rn(rsold, pAp) : 0.f;
+                xv = fmaf(step_size, p, xv);
+                r = fmaf(-step_size, Ap, r);
+                const float rsnew = warp_sum(r * r);
+                act = act && !(rsnew < tol);                       // als.cc:341
+                if (act) p = fmaf(__fdiv_rn(rsnew, rsold), p, r);  // predicated update, no branch on the team path
+                rsold = act ? rsnew : rsold;
             }
             // ---- x_blk -= delta ; Yui -= q_blk . delta  (als.cc:346-350) ----
             __syncwarp();

@@ -39,16 +39,16 @@ constexpr int GEN_WARPS = 8;
 template <int NC>
 __global__ void __launch_bounds__(GEN_WARPS * 32) als_cg_warp_kernel(AlsArgs a) {
     __shared__ float ps_all[GEN_WARPS][NC * 32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_id_uniform();
     float* ps = ps_all[wib];
     const int64_t warp0 = (int64_t)blockIdx.x * GEN_WARPS + wib;
     const int64_t nwarps = (int64_t)gridDim.x * GEN_WARPS;
     const int D = a.D, ld = a.ld;
     double l_nume = 0.0, l_deno = 0.0;
     for (int64_t ri = a.row_begin + warp0; ri < a.row_end; ri += nwarps) {
-        const int64_t row = a.row_list ? a.row_list[ri] : ri;
-        const int64_t beg = row == 0 ? 0 : a.indptr[row - 1];
-        const int64_t end = a.indptr[row];
+        const int64_t row = uni((long long)(a.row_list ? a.row_list[ri] : ri));
+        const int64_t beg = uni((long long)(row == 0 ? 0 : a.indptr[row - 1]));
+        const int64_t end = uni((long long)a.indptr[row]);
         const int64_t n = end - beg;
         if (n == 0) continue;  // als.cc:159-162: skipped, not zeroed
         float x[NC], y[NC], t[NC], r[NC], p[NC], Ap[NC];
@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_cg_warp_kernel(AlsArgs a) 
             yy += y[k] * y[k];
             rr += r[k] * r[k];
         }
-        yy = warp_sum(yy);
-        rr = warp_sum(rr);
+        yy = uni(warp_sum(yy));
+        rr = uni(warp_sum(rr));
         if (yy < rr) {  // algo.cc:64-67
 #pragma unroll
             for (int k = 0; k < NC; ++k) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_cg_warp_kernel(AlsArgs a) 
                 r[k] -= al * Ap[k];
                 rs_new += r[k] * r[k];
             }
-            rs_new = warp_sum(rs_new);
+            rs_new = uni(warp_sum(rs_new));
             if (rs_new < a.tol) break;  // algo.cc:76
             const float beta = rs_new / (rs_old + a.eps);
 #pragma unroll
@@ -210,7 +210,7 @@ template <int NC>
 __global__ void __launch_bounds__(GEN_WARPS * 32) als_ialspp_warp_kernel(AlsArgs a) {
     __shared__ float xs_all[GEN_WARPS][NC * 32];
     __shared__ float ps_all[GEN_WARPS][NC * 32];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, wib = warp_id_uniform();
     float* xs = xs_all[wib];
     float* ps = ps_all[wib];
     const int64_t warp0 = (int64_t)blockIdx.x * GEN_WARPS + wib;
@@ -219,9 +219,9 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_ialspp_warp_kernel(AlsArgs
     const int bs_opt = a.block_size < D ? a.block_size : D;  // als.cc:244
     double l_nume = 0.0, l_deno = 0.0;
     for (int64_t ri = a.row_begin + warp0; ri < a.row_end; ri += nwarps) {
-        const int64_t row = a.row_list ? a.row_list[ri] : ri;
-        const int64_t beg = row == 0 ? 0 : a.indptr[row - 1];
-        const int64_t end = a.indptr[row];
+        const int64_t row = uni((long long)(a.row_list ? a.row_list[ri] : ri));
+        const int64_t beg = uni((long long)(row == 0 ? 0 : a.indptr[row - 1]));
+        const int64_t end = uni((long long)a.indptr[row]);
         const int64_t n = end - beg;
         if (n == 0) continue;  // als.cc:289-292
         float* xrow = a.X + row * ld;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_ialspp_warp_kernel(AlsArgs
                 p[m] = bv[m];
                 rs += r[m] * r[m];
             }
-            double rsold = (double)warp_sum(rs);
+            double rsold = (double)uni(warp_sum(rs));
             if (rsold > (double)a.tol) {
                 for (int step = 0; step < 3; ++step) {  // als.cc:330
                     __syncwarp();
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_ialspp_warp_kernel(AlsArgs
                         r[m] -= step_size * Ap[m];
                         rn += r[m] * r[m];
                     }
-                    const double rsnew = (double)warp_sum(rn);
+                    const double rsnew = (double)uni(warp_sum(rn));
                     if (rsnew < (double)a.tol) break;  // als.cc:341
                     const float beta = (float)(rsnew / rsold);
 #pragma unroll
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(DIRECT_THREADS) als_direct_cta_kernel(AlsArgs 
     float* qb = wv + D;                  // [NB][D]
     __shared__ float s_v[DIRECT_NB];
     __shared__ double s_loss[2];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wid = warp_id_uniform();
     if (tid < 2) s_loss[tid] = 0.0;
     for (int64_t ri = a.row_begin + blockIdx.x; ri < a.row_end; ri += gridDim.x) {
         const int64_t row = a.row_list ? a.row_list[ri] : ri;

@@ -109,6 +109,18 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
+// Warp-uniform broadcasts: all lanes already hold the same value, but routing it through lane 0 tells the
+// compiler so; branches on the result are then uniform and shuffles under them stay plain SHFL instead of
+// WARPSYNC.COLLECTIVE calls.
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(FULL, v, 0); }
+__device__ __forceinline__ float uni(float v) { return __shfl_sync(FULL, v, 0); }
+__device__ __forceinline__ bool uni(bool v) { return __shfl_sync(FULL, (int)v, 0) != 0; }
+__device__ __forceinline__ long long uni(long long v) {
+    const int lo = __shfl_sync(FULL, (int)(v & 0xffffffffll), 0), hi = __shfl_sync(FULL, (int)(v >> 32), 0);
+    return ((long long)hi << 32) | (unsigned int)lo;
+}
+__device__ __forceinline__ int warp_id_uniform() { return __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

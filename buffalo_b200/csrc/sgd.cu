@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(SgdArgs a, const int32_t
                                                        const int32_t* __restrict__ poss,
                                                        const int32_t* __restrict__ negs, int64_t n) {
     const int lane = threadIdx.x & 31;
-    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_uniform();
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nv4 = a.ld >> 2;
     for (int64_t s = w0; s < n; s += nw) {
@@ -234,18 +234,18 @@ __device__ __forceinline__ float warp_score(const float4 (&vp)[NV], const float*
 template <int NV>
 __global__ void __launch_bounds__(256) warp_accumulate_kernel(SgdArgs a) {
     const int lane = threadIdx.x & 31;
-    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_uniform();
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nv4 = a.ld >> 2;
     double loss = 0.0;
     unsigned long long updates = 0;
     for (int64_t it = a.it_begin + w0; it < a.it_end; it += nw) {
-        const int64_t row = row_of(a.indptr, a.row_begin, a.row_end, it);
-        const int64_t beg = row == 0 ? 0 : __ldg(a.indptr + row - 1);
-        const int64_t end = __ldg(a.indptr + row);
+        const int64_t row = uni((long long)row_of(a.indptr, a.row_begin, a.row_end, it));
+        const int64_t beg = uni((long long)(row == 0 ? 0 : __ldg(a.indptr + row - 1)));
+        const int64_t end = uni((long long)__ldg(a.indptr + row));
         const int32_t* rk = a.keys + (beg - a.shift);
         const int64_t n_seen = end - beg;
-        const int pos = __ldg(a.keys + (it - a.shift));
+        const int pos = uni(__ldg(a.keys + (it - a.shift)));
         const float* pu = a.P + row * a.ld;
         const float* qi = a.Q + (int64_t)pos * a.ld;
         float4 vp[NV], vi[NV], vj[NV];
@@ -254,14 +254,14 @@ __global__ void __launch_bounds__(256) warp_accumulate_kernel(SgdArgs a) {
             const int c = lane + 32 * k;
             vp[k] = c < nv4 ? ld4(pu + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const float ui = warp_score<NV>(vp, qi, nv4, lane, a.score_l2, vi);  // warp.cc:133
+        const float ui = uni(warp_score<NV>(vp, qi, nv4, lane, a.score_l2, vi));  // warp.cc:133
         float uj = 0.f;
         int neg = 0;
         int trial = 1;
         uint32_t t = 0;
         while (trial <= a.max_trials) {  // warp.cc:137-148
             neg = draw_range(a.seed, a.epoch, (uint64_t)it, t++, (uint32_t)a.num_items);
-            if (seen_sorted(rk, n_seen, neg)) {  // :140-141, not counted as a trial
+            if (uni(seen_sorted(rk, n_seen, neg))) {  // :140-141, not counted as a trial
                 if (t > (uint32_t)(64 * a.max_trials + 4096)) {
                     trial = a.max_trials + 1;
                     break;
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) warp_accumulate_kernel(SgdArgs a) {
                 continue;
             }
             trial += 1;  // :142
-            uj = warp_score<NV>(vp, a.Q + (int64_t)neg * a.ld, nv4, lane, a.score_l2, vj);
+            uj = uni(warp_score<NV>(vp, a.Q + (int64_t)neg * a.ld, nv4, lane, a.score_l2, vj));
             if ((ui - uj) < a.threshold) break;  // :145-146
             trial += 1;  // :147
         }
@@ -363,7 +363,7 @@ __global__ void sgd_apply_kernel(int optimizer, float* __restrict__ theta, float
 // CWARP::update_parameters tail (warp.cc:194-200): row /= max(1, ||row||).  One warp per row.
 __global__ void warp_project_kernel(float* __restrict__ M, int64_t rows, int ld) {
     const int lane = threadIdx.x & 31;
-    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_uniform();
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = w0; r < rows; r += nw) {
         float* m = M + r * ld;
@@ -381,7 +381,7 @@ __global__ void probe_loss_kernel(int kind, const float* __restrict__ P, const f
                                   double threshold, const int32_t* __restrict__ us, const int32_t* __restrict__ ps,
                                   const int32_t* __restrict__ ns, int n, double* out) {
     const int lane = threadIdx.x & 31;
-    const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int w0 = blockIdx.x * (blockDim.x >> 5) + warp_id_uniform();
     const int nw = (gridDim.x * blockDim.x) >> 5;
     double acc = 0.0;
     for (int i = w0; i < n; i += nw) {
