@@ -145,30 +145,30 @@ __device__ __forceinline__ void v8_axpy(V8& acc, float cf, const V8& q) {
     for (int k = 0; k < 4; ++k) acc.v[k] = ffma2(c2, q.v[k], acc.v[k]);
 }
 
-// sum of the 8 a-lanes' acc for column b*8+k, delivered as column `lane` in lane `lane`
+// sum of the 8 a-lanes' acc for column b*8+k; lane (a,b) ends up with column b*8 + a (the a-lanes sit 4 apart)
 __device__ __forceinline__ float transposed_reduce8(const V8& acc, int la) {
     const bool h4 = la & 4, h2 = la & 2, h1 = la & 1;
-    // step xor 4: keep one float4 half, send the other
+    // first step (a bit 2): keep one float4 half, send the other
     const float2 s0 = h4 ? acc.v[0] : acc.v[2], s1 = h4 ? acc.v[1] : acc.v[3];
     const float2 k0 = h4 ? acc.v[2] : acc.v[0], k1 = h4 ? acc.v[3] : acc.v[1];
     float2 v0, v1;
-    v0.x = k0.x + __shfl_xor_sync(FULL, s0.x, 4);
-    v0.y = k0.y + __shfl_xor_sync(FULL, s0.y, 4);
-    v1.x = k1.x + __shfl_xor_sync(FULL, s1.x, 4);
-    v1.y = k1.y + __shfl_xor_sync(FULL, s1.y, 4);
-    // step xor 2
+    v0.x = k0.x + __shfl_xor_sync(FULL, s0.x, 16);
+    v0.y = k0.y + __shfl_xor_sync(FULL, s0.y, 16);
+    v1.x = k1.x + __shfl_xor_sync(FULL, s1.x, 16);
+    v1.y = k1.y + __shfl_xor_sync(FULL, s1.y, 16);
+    // second step (a bit 1)
     const float2 s = h2 ? v0 : v1, k = h2 ? v1 : v0;
     float2 u;
-    u.x = k.x + __shfl_xor_sync(FULL, s.x, 2);
-    u.y = k.y + __shfl_xor_sync(FULL, s.y, 2);
-    // step xor 1
-    return (h1 ? u.y : u.x) + __shfl_xor_sync(FULL, h1 ? u.x : u.y, 1);
+    u.x = k.x + __shfl_xor_sync(FULL, s.x, 8);
+    u.y = k.y + __shfl_xor_sync(FULL, s.y, 8);
+    // last step
+    return (h1 ? u.y : u.x) + __shfl_xor_sync(FULL, h1 ? u.x : u.y, 4);
 }
 
-// finish a block dot over the 4 b-lanes (lane bits 3,4)
+// finish a block dot over the 4 b-lanes (lane bits 0,1)
 __device__ __forceinline__ float sum_over_b(float s) {
-    s += __shfl_xor_sync(FULL, s, 8);
-    s += __shfl_xor_sync(FULL, s, 16);
+    s += __shfl_xor_sync(FULL, s, 1);
+    s += __shfl_xor_sync(FULL, s, 2);
     return s;
 }
 
@@ -201,7 +201,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     // loop, trip counts) is warp-uniform; otherwise every shuffle below is compiled as a WARPSYNC.COLLECTIVE call
     const int warp = __shfl_sync(FULL, tid >> 5, 0);
     const int team = warp / W, wt = warp % W;
-    const int la = lane & 7, lb = lane >> 3;
+    // lane = b + 4*a: the four column-group lanes of one gathered row are ADJACENT lanes, so a quarter-warp of a
+    // 128-bit gather touches 2 cache lines (not 8) -- the L1/LSU wavefront count of the gathers drops 4x
+    const int la = lane >> 2, lb = lane & 3;
+    const int mycol = lb * 8 + la;   // the column of the 32-vector this lane owns after a transposed reduction
     float* Gs = smem;
     float* stg_all = smem + (GSM ? (size_t)D * (D + 4) : 0);
     float* stg = stg_all + (size_t)warp * KT * 8 * 128;      // [KT*8 chunks][32 lanes][4 floats]
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     v8_axpy(acc, xs[i], GSM ? v8_lds(Gp + i * GP + col0) : v8_ldg(Gp + i * GP + col0));
                 }
             }
-            const float g = team_reduce(transposed_reduce8(acc, la)) + a.reg * xs[B * 32 + lane];
+            const float g = team_reduce(transposed_reduce8(acc, la)) + a.reg * xs[B * 32 + mycol];
 
             // ---- 3 CG steps on (A + sum v a q q^T) delta = g, A = G[blk,blk] + reg I (als.cc:278,324-345) ----
             // The reference skips the solve when rsold <= tol and leaves the loop when rsnew < tol (als.cc:329,341).
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
 #pragma unroll 1
             for (int step = 0; step < 3; ++step) {
                 __syncwarp();
-                pw[lane] = p;
+                pw[mycol] = p;
                 __syncwarp();
                 const V8 pc = v8_lds(pw + lb * 8);
                 acc = v8_zero();
@@ -466,7 +469,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             }
             // ---- x_blk -= delta ; Yui -= q_blk . delta  (als.cc:346-350) ----
             __syncwarp();
-            pw[lane] = xv;
+            pw[mycol] = xv;
             __syncwarp();
             const V8 xc = v8_lds(pw + lb * 8);
             for_tiles([&](int t, const V8(&qq)[4]) {
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     if (lb == 0) yui[t * 32 + la + 8 * i] -= dot;
                 }
             });
-            if (wt == 0) xs[B * 32 + lane] -= xv;
+            if (wt == 0) xs[B * 32 + mycol] -= xv;
             if (RES && KS > 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // smem-resident tiles are free only now
             team_sync<W>(team);
         }
