@@ -29,7 +29,7 @@
 
 namespace bfl {
 
-constexpr int FAST_WARPS = 24;   // 768 threads: <= 85 registers per thread, 24 warps per SM
+constexpr int FAST_WARPS = 16;   // 512 threads x 128 registers: two register tiles per warp (fewer warps per row = less redundant work)
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_NCLASS = 8;
 constexpr int FAST_NR_CAP = 12288;  // longest row the non-resident class accepts (smem for Yui/w/keys)
@@ -39,12 +39,12 @@ struct FastClass { int W, K, res, cap; };
 __host__ __device__ inline FastClass fast_class(int c) {
     switch (c) {
         case 0: return {1, 1, 1, 32};
-        case 1: return {2, 1, 1, 64};
-        case 2: return {4, 1, 1, 128};
-        case 3: return {8, 1, 1, 256};
-        case 4: return {8, 2, 1, 512};    // 1 register tile + 1 shared-memory tile per warp
-        case 5: return {24, 2, 1, 1536};  // 1 register tile + 1 shared-memory tile per warp
-        case 6: return {24, 1, 0, FAST_NR_CAP};
+        case 1: return {1, 2, 1, 64};
+        case 2: return {2, 2, 1, 128};
+        case 3: return {4, 2, 1, 256};
+        case 4: return {8, 2, 1, 512};
+        case 5: return {16, 3, 1, 1536};  // 2 register tiles + 1 shared-memory tile per warp
+        case 6: return {16, 1, 0, FAST_NR_CAP};
         default: return {0, 0, 0, 0x7fffffff};  // class 7: too long for the tuned kernels -> generic kernel
     }
 }
@@ -593,12 +593,12 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         int rc = BFL_OK;
         switch (c) {
             case 0: rc = fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 1: rc = fast_launch_class<2, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 2: rc = fast_launch_class<4, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 3: rc = fast_launch_class<8, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 4: rc = fast_launch_class<8, 1, 1, true, false>(a, fc.cap, num_sms, st); break;
-            case 5: rc = fast_launch_class<24, 1, 1, true, false>(a, fc.cap, num_sms, st); break;
-            case 6: rc = fast_launch_class<24, 1, 0, false, true>(a, fc.cap, num_sms, st); break;
+            case 1: rc = fast_launch_class<1, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 2: rc = fast_launch_class<2, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 3: rc = fast_launch_class<4, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 4: rc = fast_launch_class<8, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 5: rc = fast_launch_class<16, 2, 1, true, false>(a, fc.cap, num_sms, st); break;
+            case 6: rc = fast_launch_class<16, 1, 0, false, true>(a, fc.cap, num_sms, st); break;
         }
         if (rc != BFL_OK) return rc;
     }
