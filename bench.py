@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (tuned kernels), 1 generic kernels")
+    ap.add_argument("--exchange", default=os.environ.get("BFL_EXCHANGE", "p2p"), choices=["p2p", "allgather"],
+                    help="multi-GPU: fused peer stores from the solve kernel (default) or an NCCL all-gather per half-epoch")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.workload != "c2" or args.impl == "reference", "timing rules: warmup >= 3"
 
@@ -247,7 +249,8 @@ def main():
     obj.bind_csr(1, wl["c_indptr"], wl["c_keys"], wl["vals"])
     # contiguous row shards per rank + one in-place all-gather per half-epoch (buffalo_b200/parallel/dist.py)
     from buffalo_b200.parallel.dist import ShardedALS
-    drv = ShardedALS(obj.precompute_device, obj.update_device, P, Q, rank, world, dist if world > 1 else None)
+    drv = ShardedALS(obj.precompute_device, obj.update_device, P, Q, rank, world, dist if world > 1 else None,
+                     exchange=args.exchange, backend=obj)
     (u0, u1, _), (i0, i1, _) = drv.ranges
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -315,7 +318,10 @@ def main():
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["desc"], "users": U, "items": I, "nnz": nnz, "d": d, "optimizer": "ialspp (d>=128)",
-                      "parallelism": "row-sharded x%d, all-gather of updated factor shard per half-epoch" % world,
+                      "parallelism": ("row-sharded x%d, updated factor rows pushed to the peer replicas from inside the solve "
+                                      "kernel (P2P stores over NVLink) + 1-element all-reduce as barrier" % world)
+                      if (world > 1 and args.exchange == "p2p") else
+                      ("row-sharded x%d, NCCL all-gather of the updated factor shard per half-epoch" % world),
                       "l2_policy": "inputs (>= 16 GB) larger than L2; no explicit flush"},
            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
 

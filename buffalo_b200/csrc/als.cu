@@ -43,6 +43,8 @@ struct bfl_als {
     DevBuf<float> yui;        // generic ialspp scratch
     DevBuf<double> d_loss;    // 2 doubles
     FastCache fast_cache;     // row-length bins of the tuned path, keyed by (indptr, row range)
+    int n_peer[2] = {0, 0};   // fused multi-GPU exchange targets per axis
+    float* peers[2][BFL_MAX_PEERS] = {};
     cudaStream_t stream = nullptr;
     int num_sms = 148;
 };
@@ -148,6 +150,8 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     a.reg = axis == 0 ? h->reg_u : h->reg_i;
     a.eps = h->eps;
     a.tol = h->cg_tolerance;
+    a.n_peer = h->n_peer[axis];
+    for (int i = 0; i < BFL_MAX_PEERS; ++i) a.peerX[i] = i < a.n_peer ? h->peers[axis][i] : nullptr;
     int64_t nrows = row_end - row_begin;
 
     if (h->kernel_mode == 0 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
@@ -398,6 +402,18 @@ int bfl_als_update_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row
     if (row_begin < 0 || row_end > h->csr_rows[axis] || row_end < row_begin) BFL_FAIL(BFL_ERR_ARG, "bad row range");
     return solve_rows(h, axis, row_begin, row_end, h->d_keys[axis], h->d_vals[axis], 0, h->csr_nnz[axis], d_loss,
                       (cudaStream_t)stream);
+}
+
+int bfl_als_set_peer_replicas(bfl_als_t* h, int axis, int n_peers, float* const* peer_ptrs) {
+    if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before set_peer_replicas()");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    if (n_peers < 0 || n_peers > BFL_MAX_PEERS || (n_peers > 0 && !peer_ptrs)) BFL_FAIL(BFL_ERR_ARG, "bad peer list");
+    for (int i = 0; i < n_peers; ++i) {
+        if (!peer_ptrs[i] || ((uintptr_t)peer_ptrs[i] & 15)) BFL_FAIL(BFL_ERR_ARG, "peer pointers must be non-null, 16-byte aligned");
+        h->peers[axis][i] = peer_ptrs[i];
+    }
+    h->n_peer[axis] = n_peers;
+    return BFL_OK;
 }
 
 const float* bfl_als_gram_device(bfl_als_t* h) { return h ? h->G.p : nullptr; }

@@ -212,8 +212,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     float* xs = tb;
     float* red = xs + D;                 // [2][W][32]
     float* pw = red + 64 * W + wt * 32;  // this warp's replicated-vector scratch [32]
-    float* racc = red + 96 * W;          // [3][32] rotating shared-memory accumulators (W >= 4)
-    float* yui = racc + 96;
+    float* yui = red + 96 * W + 96;
     float* wv = yui + cap;
     int32_t* ks = reinterpret_cast<int32_t*>(wv + cap);
     const float* Gp = GSM ? Gs : a.G;    // pseudo-nnz rows come from smem or (long-row class) from L1/L2
@@ -230,34 +229,29 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     double l_nume = 0.0, l_deno = 0.0;
     int par = 0;
     const float tol = a.tol;
-    // Team-wide sum of one 32-vector (lane = column).  W <= 2: partials in smem, summed in warp order
-    // (deterministic).  W >= 4: red.shared.add into one of three rotating accumulators: every warp then reads the
-    // SAME total, so the redundant CG algebra stays bit-identical across the team (summation order, hence the last
-    // bits, may differ between runs).  Rotation: reduction k uses buffer k%3; warp 0 clears buffer (k+1)%3 before
-    // arriving at barrier k -- every warp has finished reading it because it passed barrier k-1.
-    constexpr bool ATOMIC_RED = W >= 4;
-    if (ATOMIC_RED && wt == 0) {
-        racc[lane] = 0.f; racc[32 + lane] = 0.f; racc[64 + lane] = 0.f;
-    }
+    // Team-wide sum of one 32-vector (one element per lane), deterministic (fixed warp order).
+    // W <= 2: red[par][w][lane].  W >= 4: partials grouped by four warps, red[par][w/4][lane][w%4], so that a lane
+    // collects the W partials with W/4 128-bit loads (the scalar store is a 4-way bank conflict, once per warp).
     auto team_reduce = [&](float v) -> float {
         if (W == 1) return v;
-        if (ATOMIC_RED) {
-            const int nxt = par == 2 ? 0 : par + 1;
-            if (wt == 0) racc[nxt * 32 + lane] = 0.f;
-            atomicAdd(racc + par * 32 + lane, v);
+        float tot = 0.f;
+        if (W >= 4) {
+            float* base = red + par * W * 32;
+            base[((wt >> 2) * 32 + lane) * 4 + (wt & 3)] = v;
             team_sync<W>(team);
-            const float tot = racc[par * 32 + lane];
-            par = nxt;
-            return tot;
+#pragma unroll
+            for (int g = 0; g < W / 4; ++g) {
+                const float4 p4 = lds4(base + (g * 32 + lane) * 4);
+                tot += (p4.x + p4.y) + (p4.z + p4.w);
+            }
         } else {
             red[par * W * 32 + wt * 32 + lane] = v;
             team_sync<W>(team);
-            float tot = 0.f;
 #pragma unroll
             for (int w = 0; w < W; ++w) tot += red[par * W * 32 + w * 32 + lane];
-            par ^= 1;
-            return tot;
         }
+        par ^= 1;
+        return tot;
     };
     const int64_t stride = (int64_t)gridDim.x * TEAMS;
 
@@ -302,7 +296,9 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
 
         // ---- Yui = x . q_c over all D columns (als.cc:256-266), loss pieces with the pre-update row ----
         for (int t = wt; t < ntiles; t += W) {
-            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 part2[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) part2[i] = make_float2(0.f, 0.f);
             const float* rowp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) rowp[i] = a.Y + (int64_t)ks[t * 32 + la + 8 * i] * ld + lb * 8;
@@ -312,11 +308,13 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                 for (int i = 0; i < 4; ++i) q0[i] = v8_ldg(rowp[i] + B * 32);
                 const V8 x0 = v8_lds(xs + B * 32 + lb * 8);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) part[i] += v8_dot(q0[i], x0);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) part2[i] = ffma2(q0[i].v[k], x0.v[k], part2[i]);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float dot = sum_over_b(part[i]);
+                const float dot = sum_over_b(part2[i].x + part2[i].y);
                 const int slot = t * 32 + la + 8 * i;
                 if (lb == 0 && slot < n) {
                     yui[slot] = dot;
@@ -472,16 +470,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
             pw[mycol] = xv;
             __syncwarp();
             const V8 xc = v8_lds(pw + lb * 8);
-            for_tiles([&](int t, const V8(&qq)[4]) {
-                float dots[4];
+            if (B + 1 < NB) {   // Yui is not read again after the last block
+                for_tiles([&](int t, const V8(&qq)[4]) {
+                    float dots[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], xc);
+                    for (int i = 0; i < 4; ++i) dots[i] = v8_dot(qq[i], xc);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float dot = sum_over_b(dots[i]);
-                    if (lb == 0) yui[t * 32 + la + 8 * i] -= dot;
-                }
-            });
+                    for (int i = 0; i < 4; ++i) {
+                        const float dot = sum_over_b(dots[i]);
+                        if (lb == 0) yui[t * 32 + la + 8 * i] -= dot;
+                    }
+                });
+            }
             if (wt == 0) xs[B * 32 + mycol] -= xv;
             if (RES && KS > 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // smem-resident tiles are free only now
             team_sync<W>(team);
@@ -490,7 +490,12 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
         bool bad = false;
         for (int j = lane; j < D; j += 32) bad |= !isfinite(xs[j]);
         bad = __any_sync(FULL, bad);
-        for (int j = wt * 32 + lane; j < D; j += 32 * W) xrow[j] = bad ? 0.f : xs[j];
+        for (int j = wt * 32 + lane; j < D; j += 32 * W) {
+            const float v = bad ? 0.f : xs[j];
+            xrow[j] = v;
+            // fused exchange: the same 128-byte segments go straight into the peers' replicas over NVLink
+            for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][(int64_t)row * ld + j] = v;
+        }
     }
     if (a.loss && a.compute_loss) {
         l_nume = warp_sum_d(l_nume);

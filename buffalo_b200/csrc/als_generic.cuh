@@ -29,7 +29,10 @@ struct AlsArgs {
     int max_iters;
     int adaptive_reg, compute_loss, axis;
     float alpha, reg, eps, tol;
+    int n_peer;           // fused multi-GPU exchange: every solved row is also stored to these replicas of X
+    float* peerX[15];
 };
+constexpr int BFL_MAX_PEERS = 15;
 
 constexpr int GEN_WARPS = 8;
 
@@ -193,7 +196,11 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_cg_warp_kernel(AlsArgs a) 
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const int c = lane + 32 * k;
-            if (c < D) xrow[c] = bad ? 0.f : x[k];
+            if (c < D) {
+                const float v = bad ? 0.f : x[k];
+                xrow[c] = v;
+                for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][row * ld + c] = v;
+            }
         }
         __syncwarp();
     }
@@ -394,7 +401,11 @@ __global__ void __launch_bounds__(GEN_WARPS * 32) als_ialspp_warp_kernel(AlsArgs
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const int c = lane + 32 * k;
-            if (c < D) xrow[c] = bad ? 0.f : xs[c];
+            if (c < D) {
+                const float v = bad ? 0.f : xs[c];
+                xrow[c] = v;
+                for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][row * ld + c] = v;
+            }
         }
     }
     if (a.loss && a.compute_loss && lane == 0) {
@@ -535,7 +546,11 @@ __global__ void __launch_bounds__(DIRECT_THREADS) als_direct_cta_kernel(AlsArgs 
             bool bad = false;
             for (int i = lane; i < D; i += 32) bad |= !isfinite(yv[i]);
             bad = __any_sync(FULL, bad);
-            for (int i = lane; i < D; i += 32) xrow[i] = bad ? 0.f : yv[i];
+            for (int i = lane; i < D; i += 32) {
+                const float v = bad ? 0.f : yv[i];
+                xrow[i] = v;
+                for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][row * ld + i] = v;
+            }
             if (lane == 0 && a.compute_loss) {
                 atomicAdd(&s_loss[0], l_nume);
                 atomicAdd(&s_loss[1], l_deno);

@@ -12,20 +12,55 @@ def row_shard(total, rank, world):
     return lo, min(lo + per, total), per
 
 
+def open_peer_replicas(t, rank, world, dist):
+    """CUDA-IPC exchange of one replica: returns the other ranks' copies of `t` as tensors that live on THEIR
+    GPUs but are addressable from this process (peer access over NVLink).  Same-node only."""
+    import torch
+    handle = t.untyped_storage()._share_cuda_()
+    meta = (handle, t.storage_offset(), tuple(t.shape), tuple(t.stride()))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, meta)
+    peers = []
+    for r, (h, off, shape, stride) in enumerate(gathered):
+        if r == rank:
+            continue
+        st = torch.UntypedStorage._new_shared_cuda(*h)
+        peers.append(torch.empty(0, dtype=t.dtype, device=st.device).set_(st, off, shape, stride))
+    return peers
+
+
 class ShardedALS(object):
     """precompute(axis), update(axis, row_begin, row_end): callables bound to this rank's backend;
-    P, Q: this rank's full replicas (torch tensors, updated in place by `update`)."""
+    P, Q: this rank's full replicas (torch tensors, updated in place by `update`).
 
-    def __init__(self, precompute, update, P, Q, rank=0, world=1, dist=None):
+    exchange="allgather": one in-place NCCL all-gather of the updated shard after each half-epoch.
+    exchange="p2p": fused -- the solve kernel stores every finished row into the peers' replicas itself
+    (backend.set_peer_replicas), so the transfer overlaps the solve row by row over NVLink; the only collective
+    left is a one-element all-reduce used as a stream-ordered barrier between half-epochs."""
+
+    def __init__(self, precompute, update, P, Q, rank=0, world=1, dist=None, exchange="allgather", backend=None):
         self.precompute, self.update, self.P, self.Q = precompute, update, P, Q
         self.rank, self.world, self.dist = rank, world, dist
+        self.mode = exchange if world > 1 else "none"
         self.ranges = [row_shard(P.shape[0], rank, world), row_shard(Q.shape[0], rank, world)]
         if world > 1:
             for F in (P, Q):
                 assert F.shape[0] % world == 0, "row counts must be divisible by the world size (pad the matrix)"
+        if self.mode == "p2p":
+            import torch
+            self._flag = torch.zeros(1, device=P.device)
+            self._peers = [open_peer_replicas(P, rank, world, dist), open_peer_replicas(Q, rank, world, dist)]
+            backend.set_peer_replicas(0, self._peers[0])
+            backend.set_peer_replicas(1, self._peers[1])
+            dist.barrier()
 
     def exchange(self, axis):
-        if self.world == 1:
+        if self.mode == "none":
+            return
+        if self.mode == "p2p":
+            # every rank's stores were issued by the kernels already queued on its stream; a stream-ordered
+            # collective after them is a barrier for the NEXT half-epoch's reads
+            self.dist.all_reduce(self._flag)
             return
         F = self.P if axis == 0 else self.Q
         lo, hi, _ = self.ranges[axis]

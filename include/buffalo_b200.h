@@ -106,6 +106,12 @@ int bfl_als_precompute_device(bfl_als_t* h, int axis, void* stream);
  * into d_loss[0] (numerator), d_loss[1] (denominator) (device doubles, may be NULL). */
 int bfl_als_update_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end,
                           double* d_loss, void* stream);
+/* multi-GPU fused exchange (no reference counterpart; the reference is single-device): DEVICE pointers, valid in
+ * this process (CUDA IPC / peer access), of the OTHER ranks' replicas of the matrix updated on `axis` (P for axis
+ * 0, Q for axis 1).  Every solved row is then also stored into those replicas from inside the solve kernel, so the
+ * all-gather of the updated shard overlaps the solve row by row; the caller only needs a stream-ordered barrier
+ * between half-epochs.  n_peers = 0 switches the fused exchange off.  At most 15 peers. */
+int bfl_als_set_peer_replicas(bfl_als_t* h, int axis, int n_peers, float* const* peer_ptrs);
 /* device pointer of the current Gram matrix [d x d] (tests) */
 const float* bfl_als_gram_device(bfl_als_t* h);
 /* multi-GPU: when several ranks each computed the Gram of their shard of Y, the host
