@@ -408,8 +408,23 @@ int bfl_als_set_peer_replicas(bfl_als_t* h, int axis, int n_peers, float* const*
     if (!h || !h->opt_set) BFL_FAIL(BFL_ERR_STATE, "init() must succeed before set_peer_replicas()");
     if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
     if (n_peers < 0 || n_peers > BFL_MAX_PEERS || (n_peers > 0 && !peer_ptrs)) BFL_FAIL(BFL_ERR_ARG, "bad peer list");
+    int cur = 0;
+    BFL_CUDA(cudaGetDevice(&cur));
     for (int i = 0; i < n_peers; ++i) {
         if (!peer_ptrs[i] || ((uintptr_t)peer_ptrs[i] & 15)) BFL_FAIL(BFL_ERR_ARG, "peer pointers must be non-null, 16-byte aligned");
+        // the replica lives on another GPU (mapped here through CUDA IPC): kernels of THIS device store into it,
+        // which needs peer access from the current device to the owner
+        cudaPointerAttributes attr;
+        BFL_CUDA(cudaPointerGetAttributes(&attr, peer_ptrs[i]));
+        if (attr.type != cudaMemoryTypeDevice) BFL_FAIL(BFL_ERR_ARG, "peer replica is not device memory");
+        if (attr.device != cur) {
+            int can = 0;
+            BFL_CUDA(cudaDeviceCanAccessPeer(&can, cur, attr.device));
+            if (!can) BFL_FAIL(BFL_ERR_CUDA, "no peer access from device " + std::to_string(cur) + " to " + std::to_string(attr.device));
+            cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) BFL_FAIL(BFL_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        }
         h->peers[axis][i] = peer_ptrs[i];
     }
     h->n_peer[axis] = n_peers;
