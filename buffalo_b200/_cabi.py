@@ -26,6 +26,8 @@ PROTOTYPES = {
     "bfl_abi_version": (C.c_int, []),
     "bfl_compiled_sm": (C.c_int, []),
     "bfl_kernel_launch_count": (_i64, []),
+    "bfl_ipc_open": (_vp, [_vp]),
+    "bfl_ipc_close": (C.c_int, [_vp]),
     # ALS
     "bfl_als_create": (_vp, []),
     "bfl_als_destroy": (None, [_vp]),

@@ -128,12 +128,11 @@ class CuALS(object):
         _cabi.check(self._lib.bfl_als_update_device(self._h, int(axis), int(row_begin), int(row_end), lp,
                                                     _stream_ptr(stream)), "update_device")
 
-    def set_peer_replicas(self, axis, tensors):
-        """tensors: the other ranks' replicas of the matrix updated on `axis`, opened in this process
-        (buffalo_b200.parallel.dist.open_peer_replicas); [] switches the fused exchange off."""
-        self._keep += list(tensors)
-        arr = (C.c_void_p * max(len(tensors), 1))(*[t.data_ptr() for t in tensors])
-        _cabi.check(self._lib.bfl_als_set_peer_replicas(self._h, int(axis), len(tensors), arr), "set_peer_replicas")
+    def set_peer_replicas(self, axis, pointers):
+        """pointers: device addresses (ints), valid in this process, of the other ranks' replicas of the matrix
+        updated on `axis` (buffalo_b200.parallel.dist.open_peer_replicas); [] switches the fused exchange off."""
+        arr = (C.c_void_p * max(len(pointers), 1))(*[int(p) for p in pointers])
+        _cabi.check(self._lib.bfl_als_set_peer_replicas(self._h, int(axis), len(pointers), arr), "set_peer_replicas")
 
     def gram_tensor(self):
         """View of the current d x d Gram matrix as a torch tensor (multi-GPU all-reduce, tests)."""

@@ -416,6 +416,9 @@ int bfl_als_set_peer_replicas(bfl_als_t* h, int axis, int n_peers, float* const*
         // which needs peer access from the current device to the owner
         cudaPointerAttributes attr;
         BFL_CUDA(cudaPointerGetAttributes(&attr, peer_ptrs[i]));
+        if (getenv("BFL_DEBUG"))
+            fprintf(stderr, "[bfl] peer %d axis %d ptr %p type %d device %d (current %d)\n", i, axis, (void*)peer_ptrs[i],
+                    (int)attr.type, attr.device, cur);
         if (attr.type != cudaMemoryTypeDevice) BFL_FAIL(BFL_ERR_ARG, "peer replica is not device memory");
         if (attr.device != cur) {
             int can = 0;

@@ -201,4 +201,25 @@ const char* bfl_last_error(void) { return bfl::t_last_error.c_str(); }
 int bfl_abi_version(void) { return 1; }
 int bfl_compiled_sm(void) { return 100; }
 int64_t bfl_kernel_launch_count(void) { return (int64_t)bfl::g_launches.load(); }
+void* bfl_ipc_open(const void* handle64) {
+    if (!handle64) {
+        bfl::set_error("null IPC handle");
+        return nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bfl::set_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    return base;
+}
+int bfl_ipc_close(void* base) {
+    if (!base) return BFL_OK;
+    BFL_CUDA(cudaIpcCloseMemHandle(base));
+    return BFL_OK;
+}
 }

@@ -12,21 +12,33 @@ def row_shard(total, rank, world):
     return lo, min(lo + per, total), per
 
 
+_opened = {}   # IPC handle bytes -> mapped base address (a handle may be opened once per process)
+
+
 def open_peer_replicas(t, rank, world, dist):
-    """CUDA-IPC exchange of one replica: returns the other ranks' copies of `t` as tensors that live on THEIR
-    GPUs but are addressable from this process (peer access over NVLink).  Same-node only."""
-    import torch
-    handle = t.untyped_storage()._share_cuda_()
-    meta = (handle, t.storage_offset(), tuple(t.shape), tuple(t.stride()))
+    """CUDA-IPC exchange of one replica: returns the device addresses, valid in THIS process with the current
+    device as accessor, of the other ranks' copies of `t` (same node, peer access over NVLink).  The owner exports
+    its allocation with torch's `_share_cuda_` (IPC handle of the cudaMalloc block + byte offset); the mapping is
+    opened by the C library so that it belongs to the local device's context."""
+    import ctypes as C
+
+    from buffalo_b200 import _cabi
+    _, handle, _, offset_bytes, *_rest = t.untyped_storage()._share_cuda_()
+    meta = (bytes(handle), int(offset_bytes) + t.storage_offset() * t.element_size())
     gathered = [None] * world
     dist.all_gather_object(gathered, meta)
-    peers = []
-    for r, (h, off, shape, stride) in enumerate(gathered):
+    ptrs = []
+    for r, (h, off) in enumerate(gathered):
         if r == rank:
             continue
-        st = torch.UntypedStorage._new_shared_cuda(*h)
-        peers.append(torch.empty(0, dtype=t.dtype, device=st.device).set_(st, off, shape, stride))
-    return peers
+        if h not in _opened:
+            buf = C.create_string_buffer(h, len(h))
+            base = _cabi.lib().bfl_ipc_open(buf)
+            if not base:
+                raise _cabi.BackendError("bfl_ipc_open: " + _cabi.lib().bfl_last_error().decode())
+            _opened[h] = base
+        ptrs.append(_opened[h] + off)
+    return ptrs
 
 
 class ShardedALS(object):

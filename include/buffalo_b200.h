@@ -47,6 +47,12 @@ int bfl_abi_version(void);
 int bfl_compiled_sm(void);
 /* number of kernels this library launched since load (bench.py's gpu_launches claim) */
 int64_t bfl_kernel_launch_count(void);
+/* Map another process's device allocation into this process with the CURRENT device as accessor
+ * (cudaIpcOpenMemHandle + lazy peer access): `handle64` is the 64-byte cudaIpcMemHandle_t exported by the owner.
+ * Returns the base address of the allocation (NULL on failure, see bfl_last_error).  Used by the fused multi-GPU
+ * exchange; a handle must be opened at most once per process. */
+void* bfl_ipc_open(const void* handle64);
+int bfl_ipc_close(void* base);
 
 /* ======================================================================================
  * ALS  -- replaces CyALS (buffalo/algo/_als.pyx:28-63 -> als::CALS, lib/algo_impl/als/als.cc)
