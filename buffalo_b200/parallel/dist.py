@@ -24,7 +24,12 @@ def open_peer_replicas(t, rank, world, dist):
 
     from buffalo_b200 import _cabi
     _, handle, _, offset_bytes, *_rest = t.untyped_storage()._share_cuda_()
-    meta = (bytes(handle), int(offset_bytes) + t.storage_offset() * t.element_size())
+    handle = bytes(handle)
+    if len(handle) == 65:      # recent torch prefixes the cudaIpcMemHandle_t with a one-byte allocation-kind tag
+        handle = handle[1:]
+    if len(handle) != 64:
+        raise RuntimeError("unexpected CUDA IPC handle size %d (expandable segments are not shareable)" % len(handle))
+    meta = (handle, int(offset_bytes) + t.storage_offset() * t.element_size())
     gathered = [None] * world
     dist.all_gather_object(gathered, meta)
     ptrs = []
