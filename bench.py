@@ -242,6 +242,9 @@ def main():
     if rank == 0:
         log("workload built in %.1fs: U=%d I=%d nnz=%d d=%d" % (time.perf_counter() - t_setup, U, I, nnz, d))
 
+    if world > 1 and args.exchange == "p2p":
+        from buffalo_b200.parallel.dist import exportable_like
+        P, Q = exportable_like(P), exportable_like(Q)
     obj = backend.CuALS()
     assert obj.init(opt), obj.last_error
     obj.bind_factors(P, Q)

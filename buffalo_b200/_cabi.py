@@ -28,6 +28,9 @@ PROTOTYPES = {
     "bfl_kernel_launch_count": (_i64, []),
     "bfl_ipc_open": (_vp, [_vp]),
     "bfl_ipc_close": (C.c_int, [_vp]),
+    "bfl_dev_alloc": (_vp, [_sz]),
+    "bfl_dev_free": (C.c_int, [_vp]),
+    "bfl_ipc_export": (C.c_int, [_vp, _vp]),
     # ALS
     "bfl_als_create": (_vp, []),
     "bfl_als_destroy": (None, [_vp]),

@@ -217,6 +217,28 @@ void* bfl_ipc_open(const void* handle64) {
     }
     return base;
 }
+void* bfl_dev_alloc(size_t bytes) {
+    if (bfl::require_device() != BFL_OK) return nullptr;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        bfl::set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        return nullptr;
+    }
+    return p;
+}
+int bfl_dev_free(void* p) {
+    if (p) BFL_CUDA(cudaFree(p));
+    return BFL_OK;
+}
+int bfl_ipc_export(void* dev_ptr, void* out_handle64) {
+    if (!dev_ptr || !out_handle64) BFL_FAIL(BFL_ERR_ARG, "null argument");
+    cudaIpcMemHandle_t h;
+    BFL_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(out_handle64, &h, sizeof(h));
+    return BFL_OK;
+}
 int bfl_ipc_close(void* base) {
     if (!base) return BFL_OK;
     BFL_CUDA(cudaIpcCloseMemHandle(base));

@@ -13,36 +13,65 @@ def row_shard(total, rank, world):
 
 
 _opened = {}   # IPC handle bytes -> mapped base address (a handle may be opened once per process)
+_exportable = {}   # data_ptr -> owner object keeping the cudaMalloc buffer alive
+
+
+class _DevBuffer(object):
+    """A plain cudaMalloc buffer owned by the C library (its IPC handle refers to exactly this buffer), exposed to
+    torch through __cuda_array_interface__."""
+
+    def __init__(self, shape):
+        from buffalo_b200 import _cabi
+        self.shape = tuple(int(x) for x in shape)
+        n = 1
+        for x in self.shape:
+            n *= x
+        self._lib = _cabi.lib()
+        self.ptr = self._lib.bfl_dev_alloc(n * 4)
+        if not self.ptr:
+            raise _cabi.BackendError("bfl_dev_alloc: " + self._lib.bfl_last_error().decode())
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 2}
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            self._lib.bfl_dev_free(self.ptr)
+            self.ptr = None
+
+
+def exportable_like(t):
+    """Copy of the float32 CUDA tensor `t` in an IPC-exportable buffer (torch's caching allocator sub-allocates and
+    tags its handles; a dedicated cudaMalloc keeps the exchange independent of torch internals)."""
+    import torch
+    buf = _DevBuffer(t.shape)
+    out = torch.as_tensor(buf, device=t.device)
+    out.copy_(t)
+    _exportable[out.data_ptr()] = buf
+    return out
 
 
 def open_peer_replicas(t, rank, world, dist):
     """CUDA-IPC exchange of one replica: returns the device addresses, valid in THIS process with the current
-    device as accessor, of the other ranks' copies of `t` (same node, peer access over NVLink).  The owner exports
-    its allocation with torch's `_share_cuda_` (IPC handle of the cudaMalloc block + byte offset); the mapping is
-    opened by the C library so that it belongs to the local device's context."""
+    device as accessor, of the other ranks' copies of `t` (same node, peer access over NVLink).  `t` must come
+    from exportable_like()."""
     import ctypes as C
 
     from buffalo_b200 import _cabi
-    _, handle, _, offset_bytes, *_rest = t.untyped_storage()._share_cuda_()
-    handle = bytes(handle)
-    if len(handle) == 65:      # recent torch prefixes the cudaIpcMemHandle_t with a one-byte allocation-kind tag
-        handle = handle[1:]
-    if len(handle) != 64:
-        raise RuntimeError("unexpected CUDA IPC handle size %d (expandable segments are not shareable)" % len(handle))
-    meta = (handle, int(offset_bytes) + t.storage_offset() * t.element_size())
+    assert t.data_ptr() in _exportable, "replicas of the fused exchange must be allocated with exportable_like()"
+    lib = _cabi.lib()
+    mine = C.create_string_buffer(64)
+    _cabi.check(lib.bfl_ipc_export(t.data_ptr(), mine), "bfl_ipc_export")
     gathered = [None] * world
-    dist.all_gather_object(gathered, meta)
+    dist.all_gather_object(gathered, mine.raw)
     ptrs = []
-    for r, (h, off) in enumerate(gathered):
+    for r, h in enumerate(gathered):
         if r == rank:
             continue
         if h not in _opened:
-            buf = C.create_string_buffer(h, len(h))
-            base = _cabi.lib().bfl_ipc_open(buf)
+            base = lib.bfl_ipc_open(C.create_string_buffer(h, 64))
             if not base:
-                raise _cabi.BackendError("bfl_ipc_open: " + _cabi.lib().bfl_last_error().decode())
+                raise _cabi.BackendError("bfl_ipc_open: " + lib.bfl_last_error().decode())
             _opened[h] = base
-        ptrs.append(_opened[h] + off)
+        ptrs.append(_opened[h])
     return ptrs
 
 

@@ -53,6 +53,11 @@ int64_t bfl_kernel_launch_count(void);
  * exchange; a handle must be opened at most once per process. */
 void* bfl_ipc_open(const void* handle64);
 int bfl_ipc_close(void* base);
+/* Device allocations that can be exported to other processes (plain cudaMalloc, so the IPC handle refers to
+ * exactly this buffer): used for the factor replicas of the fused multi-GPU exchange. */
+void* bfl_dev_alloc(size_t bytes);
+int bfl_dev_free(void* p);
+int bfl_ipc_export(void* dev_ptr, void* out_handle64);
 
 /* ======================================================================================
  * ALS  -- replaces CyALS (buffalo/algo/_als.pyx:28-63 -> als::CALS, lib/algo_impl/als/als.cc)

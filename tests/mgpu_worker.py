@@ -20,6 +20,9 @@ def run(world, rank, mode, P0, Q0, rw, cw, dev, d):
     obj = backend.CuALS()
     assert obj.init(opt)
     P, Q = torch.from_numpy(P0.copy()).to(dev), torch.from_numpy(Q0.copy()).to(dev)
+    if mode == "p2p":
+        from buffalo_b200.parallel.dist import exportable_like
+        P, Q = exportable_like(P), exportable_like(Q)
     obj.bind_factors(P, Q)
     t = lambda a: torch.from_numpy(a).to(dev)  # noqa: E731
     obj.bind_csr(0, t(rw[0]), t(rw[1]), t(rw[2]))
