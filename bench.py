@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (tuned kernels), 1 generic kernels")
+    ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (tuned SIMT kernels), 1 generic kernels, 3 tensor-core Gram variant")
     ap.add_argument("--exchange", default=os.environ.get("BFL_EXCHANGE", "p2p"), choices=["p2p", "allgather"],
                     help="multi-GPU: fused peer stores from the solve kernel (default) or an NCCL all-gather per half-epoch")
     args = ap.parse_args()

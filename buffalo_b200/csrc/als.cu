@@ -1,6 +1,6 @@
 // ALS backend: host-side state machine + C ABI (see include/buffalo_b200.h).
 // Replaces als::CALS (lib/algo_impl/als/als.cc) / cuda_als::CuALS (lib/cuda/als/als.cu).
-#include "als_fast.cuh"
+#include "als_mma.cuh"
 #include "als_generic.cuh"
 #include "bfl_common.cuh"
 
@@ -15,7 +15,7 @@ struct bfl_als {
     int block_size = 32;
     bool adaptive_reg = false, compute_loss = true;
     float alpha = 8.f, reg_u = 0.1f, reg_i = 0.1f, eps = 1e-10f, cg_tolerance = 1e-10f;
-    int kernel_mode = 0;  // 0 auto (tuned kernels when applicable), 1 force generic
+    int kernel_mode = 0;  // 0 auto (tuned SIMT kernels when applicable), 1 force generic, 3 tensor-core Gram variant (als_mma.cuh)
 
     // factors: either owned device mirrors of retained host pointers, or borrowed device memory
     float* hostP = nullptr;
@@ -154,10 +154,10 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     for (int i = 0; i < BFL_MAX_PEERS; ++i) a.peerX[i] = i < a.n_peer ? h->peers[axis][i] : nullptr;
     int64_t nrows = row_end - row_begin;
 
-    if (h->kernel_mode == 0 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
+    if (h->kernel_mode != 1 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
         const int32_t* left = nullptr;
         int64_t nleft = 0;
-        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft);
+        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, h->kernel_mode == 3);
         if (rc != BFL_OK || nleft == 0) return rc;
         // rows longer than the tuned kernels accept go through the generic kernel
         a.row_list = left;

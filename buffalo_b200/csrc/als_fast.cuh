@@ -508,6 +508,10 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
 }
 
 // ---- host side --------------------------------------------------------------------------------
+// tensor-core variant (als_mma.cuh)
+inline bool mma_class_covered(int c);
+inline int mma_launch(int c, const AlsArgs& a, int cap, int num_sms, cudaStream_t st);
+
 struct FastBins {
     DevBuf<int32_t> lists;           // all classes back to back
     DevBuf<unsigned int> counters;   // [0..7] counts, [8..15] cursors
@@ -557,7 +561,7 @@ int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
 // bins rows [row_begin,row_end) of a.indptr by length (cached per (indptr,row range)) and launches one
 // kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`
 inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cudaStream_t st,
-                           const int32_t** leftover_rows, int64_t* leftover_count) {
+                           const int32_t** leftover_rows, int64_t* leftover_count, bool use_mma) {
     *leftover_rows = nullptr;
     *leftover_count = 0;
     const int64_t nrows = a0.row_end - a0.row_begin;
@@ -596,6 +600,11 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         a.row_end = fb->offset[c + 1];
         const FastClass fc = fast_class(c);
         int rc = BFL_OK;
+        if (use_mma && mma_class_covered(c)) {
+            rc = mma_launch(c, a, fc.cap, num_sms, st);
+            if (rc != BFL_OK) return rc;
+            continue;
+        }
         switch (c) {
             case 0: rc = fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
             case 1: rc = fast_launch_class<1, 2, 0, true, true>(a, fc.cap, num_sms, st); break;

@@ -105,6 +105,8 @@ __global__ void bpr_sample_kernel(SgdArgs a, int32_t* __restrict__ out_u, int32_
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// L2-coherent read: rows are being updated by atomics from other SMs (and by this warp's previous triple)
+__device__ __forceinline__ float4 ld4_cg(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void red4(float* p, float4 v) { atomicAdd(reinterpret_cast<float4*>(p), v); }
 
 // ---------------------------------------------------------------------------------------
@@ -122,7 +124,12 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(SgdArgs a, const int32_t
     const int64_t w0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp_id_uniform();
     const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int nv4 = a.ld >> 2;
-    for (int64_t s = w0; s < n; s += nw) {
+    // Each warp walks a CONTIGUOUS range of triples one after the other, like a worker thread of the reference
+    // walks its job's rows (bpr.cc:103-117): the positives of one user are applied sequentially and concurrent
+    // warps work on different users, so only item rows are shared Hogwild-style.
+    const int64_t per = (n + nw - 1) / nw;
+    const int64_t s_end = (w0 + 1) * per < n ? (w0 + 1) * per : n;
+    for (int64_t s = w0 * per; s < s_end; ++s) {
         const int u = __ldg(us + s), pos = __ldg(poss + s), neg = __ldg(negs + s);
         float* pu = a.P + (int64_t)u * a.ld;
         float* qi = a.Q + (int64_t)pos * a.ld;
@@ -133,9 +140,9 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(SgdArgs a, const int32_t
         for (int k = 0; k < NV; ++k) {
             const int c = lane + 32 * k;
             if (c < nv4) {
-                vp[k] = ld4(pu + 4 * c);
-                vi[k] = ld4(qi + 4 * c);
-                vj[k] = ld4(qj + 4 * c);
+                vp[k] = ld4_cg(pu + 4 * c);
+                vi[k] = ld4_cg(qi + 4 * c);
+                vj[k] = ld4_cg(qj + 4 * c);
                 part += vp[k].x * (vi[k].x - vj[k].x) + vp[k].y * (vi[k].y - vj[k].y) +
                         vp[k].z * (vi[k].z - vj[k].z) + vp[k].w * (vi[k].w - vj[k].w);
             }
@@ -143,8 +150,8 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(SgdArgs a, const int32_t
         float x = warp_sum(part);  // bpr.cc:119
         float bi = 0.f, bj = 0.f;
         if (a.use_bias) {
-            bi = a.Qb[pos];
-            bj = a.Qb[neg];
+            bi = __ldcg(a.Qb + pos);
+            bj = __ldcg(a.Qb + neg);
             x += bi - bj;  // bpr.cc:120-121
         }
         // logit = 1 - sigmoid(x) with the reference's clamp at +-MAX_EXP = 6 (bpr.cc:123-131; the exact
@@ -553,7 +560,8 @@ void fill_args(bfl_sgd* h, SgdArgs& a, const int32_t* keys, int64_t shift, int64
 int launch_bpr_apply(bfl_sgd* h, const SgdArgs& a, const int32_t* u, const int32_t* p, const int32_t* n, int64_t cnt,
                      cudaStream_t st) {
     if (cnt <= 0) return BFL_OK;
-    const int grid = (int)std::min<int64_t>((cnt + 7) / 8, (int64_t)h->num_sms * 16);
+    // >= 16 consecutive triples per warp, at most 32 warps per SM (staleness grows with the number of triples in flight)
+    const int grid = (int)std::min<int64_t>((cnt + 127) / 128, (int64_t)h->num_sms * 4);
     const int nv = (h->vdim / 4 + 31) / 32;
     if (nv <= 1) bpr_apply_kernel<1><<<grid, 256, 0, st>>>(a, u, p, n, cnt);
     else if (nv <= 2) bpr_apply_kernel<2><<<grid, 256, 0, st>>>(a, u, p, n, cnt);

@@ -137,8 +137,9 @@ def test_c1_config_training_trajectory(cuda_lib):
 
 @pytest.mark.parametrize("d", [128, 64, 32])
 def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
-    """The tuned iALS++ kernel bins rows by length (<=32, 64, 128, 256, 512 register-resident; <=1536 two register
-    tiles + one shared-memory tile per warp; <=12288 re-gathering; longer rows fall back to the generic kernel).
+    """The tuned iALS++ kernels bin rows by length (<=32, 64, 128, 256, 512 register-resident; <=1536 two register
+    tiles + one shared-memory tile per warp, SIMT kernel by default, tensor-core Gram variant with
+    _b200_kernel_mode=3; <=12288 re-gathering SIMT kernel; longer rows fall back to the generic kernel).
     One input that hits every class, checked against the oracle and the generic kernel (_b200_kernel_mode=1)."""
     rng = np.random.default_rng(d)
     lengths = np.concatenate([rng.integers(1, 33, 300), rng.integers(33, 65, 200), rng.integers(65, 129, 150),
@@ -158,9 +159,21 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
         X0, n0, dn0 = oracle_half(o, P, Q, indptr, keys, vals, 0)
         Xf, nf, dnf = gpu_half(o, P, Q, indptr, keys, vals, 0)
         Xg, ng, dng = gpu_half(dict(o, _b200_kernel_mode=1), P, Q, indptr, keys, vals, 0)
-        assert rel_err(Xf, X0) < FACTOR_TOL and rel_err(Xg, X0) < FACTOR_TOL
+        Xs, ns, dns = gpu_half(dict(o, _b200_kernel_mode=3), P, Q, indptr, keys, vals, 0)   # tensor-core Gram variant
+        assert rel_err(Xf, X0) < FACTOR_TOL and rel_err(Xg, X0) < FACTOR_TOL and rel_err(Xs, X0) < FACTOR_TOL
         assert rel_err(Xf, Xg) < FACTOR_TOL
+        # no single row is off either (the Frobenius norm would hide one bad row-length class)
+        row_err = np.linalg.norm(Xf - X0, axis=1) / np.maximum(np.linalg.norm(X0, axis=1), 1e-6)
+        assert row_err.max() < 5e-3, (int(row_err.argmax()), int(lengths[row_err.argmax()]), float(row_err.max()))
         check_loss(nf, dnf, n0, dn0)
+        check_loss(ns, dns, n0, dn0)
+    # negative confidence values are legal input for every kernel variant
+    vneg = vals.copy()
+    vneg[::7] *= -0.25
+    X0, n0, dn0 = oracle_half(opt, P, Q, indptr, keys, vneg, 0)
+    for mode in (0, 3):
+        Xf, nf, dnf = gpu_half(dict(opt, _b200_kernel_mode=mode), P, Q, indptr, keys, vneg, 0)
+        assert np.isfinite(Xf).all() and rel_err(Xf, X0) < FACTOR_TOL, mode
     # item side (loss has the extra x G x and observed terms): reuse the same CSR as a colwise matrix
     Pi = init_factors(I, d, d, 3, scale=0.05, signed=True)      # "users" are now the opposite side
     Qi = init_factors(U, d, d, 4, scale=0.05, signed=True)      # rows being updated (axis 1)
