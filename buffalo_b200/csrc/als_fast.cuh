@@ -17,9 +17,10 @@
 //     (L2 hits);
 //   * the dense terms x.G[:,blk] and A p are expressed as extra "pseudo-nnz" tiles whose rows come from the
 //     Gram matrix held in shared memory, distributed over the team's warps;
-//   * per-row state (x, Yui, alpha*v, keys) lives in shared memory; the CG vector algebra is executed
-//     redundantly by every warp of the team from the same reduced partials (bit-identical, so all warps
-//     take the same early-exit decisions) with one named barrier per reduction.
+//   * per-row state (x, Yui, alpha*v, keys) lives in shared memory; every warp contributes its tiles' partial
+//     of a team-wide 32-vector, the team's first warp (the solver) adds the partials up, runs the CG scalar
+//     recurrences and publishes the next direction -- two named barriers per reduction, no replicated algebra
+//     (the shuffles and shared-memory reads of that algebra, not the FMAs, are what the team kernels are bound by).
 #pragma once
 #include <algorithm>
 #include <map>
@@ -181,7 +182,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 // dynamic smem layout:
 //   [GSM ? Gs[D*(D+4)] : -] | staging: 16 warps x (K+KS)*8 chunks x 32 lanes x 16 B (RES only) |
-//   per team: xs[D] red[2*W*32] pw[W*32] racc[3*32] yui[cap] wv[cap] ks[cap]
+//   per team: xs[D] red[2*W*32] pvec[32] (W*32 reserved) dl[32] (96 reserved) yui[cap] wv[cap] ks[cap]
 __host__ __device__ inline size_t fast_team_floats(int D, int W, int cap) { return (size_t)D + 96 * W + 96 + 3 * (size_t)cap; }
 __host__ __device__ inline size_t fast_smem_bytes(int D, int W, int K, int KS, bool res, bool gsm, int cap) {
     return sizeof(float) * ((gsm ? (size_t)D * (D + 4) : 0) + (res ? (size_t)FAST_WARPS * (K + KS) * 8 * 128 : 0) +
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     float* tb = stg_all + (RES ? (size_t)FAST_WARPS * KT * 8 * 128 : 0) + (size_t)team * fast_team_floats(D, W, cap);
     float* xs = tb;
     float* red = xs + D;                 // [2][W][32]
-    float* pw = red + 64 * W + wt * 32;  // this warp's replicated-vector scratch [32]
+    float* pvec = red + 64 * W;          // the CG direction, published by the solver warp
+    float* dl = red + 96 * W;            // the block's solution delta
     float* yui = red + 96 * W + 96;
     float* wv = yui + cap;
     int32_t* ks = reinterpret_cast<int32_t*>(wv + cap);
@@ -227,38 +229,40 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
     }
 
     double l_nume = 0.0, l_deno = 0.0;
-    int par = 0;
     const float tol = a.tol;
-    // Team-wide sum of one 32-vector (one element per lane), deterministic (fixed warp order).
-    // W <= 2: red[par][w][lane].  W >= 4: partials grouped by four warps, red[par][w/4][lane][w%4], so that a lane
+    // Team-wide sum of one 32-vector (one element per lane), deterministic (fixed warp order): every warp stores its
+    // partial, and after a team barrier the solver warp (wt == 0) adds them up.
+    // W <= 2: red[w][lane].  W >= 4: partials grouped by four warps, red[w/4][lane][w%4], so that the solver
     // collects the W partials with W/4 128-bit loads (the scalar store is a 4-way bank conflict, once per warp).
-    auto team_reduce = [&](float v) -> float {
+    auto store_partial = [&](float v) {
+        if (W == 1) return;
+        if (W >= 4) red[((wt >> 2) * 32 + lane) * 4 + (wt & 3)] = v;
+        else red[wt * 32 + lane] = v;
+    };
+    auto solver_total = [&](float v) -> float {
         if (W == 1) return v;
         float tot = 0.f;
         if (W >= 4) {
-            float* base = red + par * W * 32;
-            base[((wt >> 2) * 32 + lane) * 4 + (wt & 3)] = v;
-            team_sync<W>(team);
 #pragma unroll
             for (int g = 0; g < W / 4; ++g) {
-                const float4 p4 = lds4(base + (g * 32 + lane) * 4);
+                const float4 p4 = lds4(red + (g * 32 + lane) * 4);
                 tot += (p4.x + p4.y) + (p4.z + p4.w);
             }
         } else {
-            red[par * W * 32 + wt * 32 + lane] = v;
-            team_sync<W>(team);
 #pragma unroll
-            for (int w = 0; w < W; ++w) tot += red[par * W * 32 + w * 32 + lane];
+            for (int w = 0; w < W; ++w) tot += red[w * 32 + lane];
         }
-        par ^= 1;
         return tot;
     };
     const int64_t stride = (int64_t)gridDim.x * TEAMS;
 
-    // issue the async copies of this lane's patch of column block B for tiles [kk0, kk1)
-    auto stage_block = [&](int B, int ntiles) {
+    // issue the async copies of this lane's patch of column block B; reg_tiles / smem_tiles select the tiles.  The
+    // staging cells of a register tile are free as soon as the block has read them back, those of a shared-memory
+    // tile only after the block's last pass.
+    auto stage_block = [&](int B, int ntiles, bool reg_tiles, bool smem_tiles) {
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
+            if (kk < K ? !reg_tiles : !smem_tiles) continue;
             const int t = wt + kk * W;
             if (kk < K || t < ntiles) {   // register tiles: always (padded slots gather a valid row, weight 0)
 #pragma unroll
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
         }
         for (int j = wt * 32 + lane; j < D; j += 32 * W) xs[j] = xrow[j];
         team_sync<W>(team);
-        if (RES) stage_block(0, ntiles);   // block 0's segments fly while the Yui pass streams the rows
+        if (RES) stage_block(0, ntiles, true, true);   // block 0's segments fly while the Yui pass streams the rows
 
         // ---- Yui = x . q_c over all D columns (als.cc:256-266), loss pieces with the pre-update row ----
         for (int t = wt; t < ntiles; t += W) {
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                         const float* src = stg + ((kk * 4 + i) * 2) * 128 + lane * 4;
                         q[kk][i] = v8_from(lds4(src), lds4(src + 128));
                     }
-                if (KS == 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // prefetch the next block behind the math
+                if (B + 1 < NB) stage_block(B + 1, ntiles, true, false);   // prefetch the next block behind the math
             }
             // per-pass visitor over this warp's tiles: register tiles, smem-resident tiles, or re-gathered tiles
             auto for_tiles = [&](auto&& body) {
@@ -420,21 +424,28 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     v8_axpy(acc, xs[i], GSM ? v8_lds(Gp + i * GP + col0) : v8_ldg(Gp + i * GP + col0));
                 }
             }
-            const float g = team_reduce(transposed_reduce8(acc, la)) + a.reg * xs[B * 32 + mycol];
+            const float gpart = transposed_reduce8(acc, la);
+            store_partial(gpart);
+            team_sync<W>(team);
 
             // ---- 3 CG steps on (A + sum v a q q^T) delta = g, A = G[blk,blk] + reg I (als.cc:278,324-345) ----
             // The reference skips the solve when rsold <= tol and leaves the loop when rsnew < tol (als.cc:329,341).
             // Here the three steps always run and those conditions only mask the updates: identical results, no
-            // data-dependent branch around the shuffles / team barriers.
-            float xv = 0.f, r = g, p = g;
-            float rsold = warp_sum(r * r);
-            bool act = rsold > tol;
+            // data-dependent branch around the shuffles / team barriers.  The recurrences live in the solver warp.
+            float xv = 0.f, r = 0.f, p = 0.f, rsold = 0.f;
+            bool act = false;
+            if (wt == 0) {
+                const float g = solver_total(gpart) + a.reg * xs[B * 32 + mycol];
+                r = g;
+                p = g;
+                rsold = warp_sum(r * r);
+                act = rsold > tol;
+                pvec[mycol] = p;
+            }
+            team_sync<W>(team);
 #pragma unroll 1
             for (int step = 0; step < 3; ++step) {
-                __syncwarp();
-                pw[mycol] = p;
-                __syncwarp();
-                const V8 pc = v8_lds(pw + lb * 8);
+                const V8 pc = v8_lds(pvec + lb * 8);
                 acc = v8_zero();
                 for_tiles([&](int t, const V8(&qq)[4]) {
                     float dots[4];
@@ -450,26 +461,35 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     for (int m = 0; m < 4; ++m) {
                         const int i = la + 8 * m;
                         const float* gr = Gp + (B * 32 + i) * GP + col0;
-                        v8_axpy(acc, pw[i], GSM ? v8_lds(gr) : v8_ldg(gr));
+                        v8_axpy(acc, pvec[i], GSM ? v8_lds(gr) : v8_ldg(gr));
                     }
                 }
-                const float Ap = team_reduce(transposed_reduce8(acc, la)) + a.reg * p;
-                const float pAp = warp_sum(p * Ap);
-                // als.cc:337 (no eps): the reference divides a double holding a float by a float and rounds to
-                // float; an fp32 division of the same two floats gives that quotient (up to double rounding)
-                const float step_size = act ? __fdiv_rn(rsold, pAp) : 0.f;
-                xv = fmaf(step_size, p, xv);
-                r = fmaf(-step_size, Ap, r);
-                const float rsnew = warp_sum(r * r);
-                act = act && !(rsnew < tol);                       // als.cc:341
-                if (act) p = fmaf(__fdiv_rn(rsnew, rsold), p, r);  // predicated update, no branch on the team path
-                rsold = act ? rsnew : rsold;
+                const float part = transposed_reduce8(acc, la);
+                store_partial(part);
+                team_sync<W>(team);   // all partials stored, and everybody has read this step's direction
+                if (wt == 0) {
+                    const float Ap = solver_total(part) + a.reg * p;
+                    const float pAp = warp_sum(p * Ap);
+                    // als.cc:337 (no eps): the reference divides a double holding a float by a float and rounds to
+                    // float; the fast fp32 division (reciprocal + multiply, <= 2 ulp) is far inside the parity bar
+                    const float step_size = act ? __fdividef(rsold, pAp) : 0.f;
+                    xv = fmaf(step_size, p, xv);
+                    r = fmaf(-step_size, Ap, r);
+                    const float rsnew = warp_sum(r * r);
+                    act = act && !(rsnew < tol);                          // als.cc:341
+                    if (act) p = fmaf(__fdividef(rsnew, rsold), p, r);   // predicated update
+                    rsold = act ? rsnew : rsold;
+                    if (step < 2) {
+                        pvec[mycol] = p;
+                    } else {   // x_blk -= delta (als.cc:346)
+                        dl[mycol] = xv;
+                        xs[B * 32 + mycol] -= xv;
+                    }
+                }
+                team_sync<W>(team);   // the next direction (or the block's delta) is published
             }
-            // ---- x_blk -= delta ; Yui -= q_blk . delta  (als.cc:346-350) ----
-            __syncwarp();
-            pw[mycol] = xv;
-            __syncwarp();
-            const V8 xc = v8_lds(pw + lb * 8);
+            // ---- Yui -= q_blk . delta  (als.cc:347-350) ----
+            const V8 xc = v8_lds(dl + lb * 8);
             if (B + 1 < NB) {   // Yui is not read again after the last block
                 for_tiles([&](int t, const V8(&qq)[4]) {
                     float dots[4];
@@ -482,9 +502,8 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
                     }
                 });
             }
-            if (wt == 0) xs[B * 32 + mycol] -= xv;
-            if (RES && KS > 0 && B + 1 < NB) stage_block(B + 1, ntiles);   // smem-resident tiles are free only now
-            team_sync<W>(team);
+            if (RES && KS > 0 && B + 1 < NB) stage_block(B + 1, ntiles, false, true);   // smem-resident tiles are free only now
+            __syncwarp();   // the next block reads Yui slots written by other lanes of this warp
         }
         // NaN/Inf guard (cf. als.cu:116-120), then write the row back
         bool bad = false;
