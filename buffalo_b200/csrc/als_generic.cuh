@@ -567,62 +567,99 @@ __global__ void __launch_bounds__(DIRECT_THREADS) als_direct_cta_kernel(AlsArgs 
 // slab over its share of the rows in registers (8x8 per thread), writes a partial, and a second
 // kernel sums the partials in fp64.
 // ---------------------------------------------------------------------------------------
+// packed fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves
+__device__ __forceinline__ float2 gram_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
 constexpr int GRAM_TR = 32;       // rows per smem tile
 constexpr int GRAM_THREADS = 256;
 
-__global__ void __launch_bounds__(GRAM_THREADS) gram_partial_kernel(const float* __restrict__ F, int64_t rows,
+__global__ void __launch_bounds__(GRAM_THREADS, 2) gram_partial_kernel(const float* __restrict__ F, int64_t rows,
                                                                     int D, int ld, float* __restrict__ partial,
                                                                     int nslab) {
-    // blockIdx.y enumerates (si, sj) output slabs of 128x128; blockIdx.x strides over row tiles
-    __shared__ float sa[GRAM_TR][128 + 4];
-    __shared__ float sb[GRAM_TR][128 + 4];
+    // blockIdx.y enumerates (si, sj) output slabs of 128x128; blockIdx.x strides over row tiles.
+    // The next row tile is fetched into registers (128-bit loads) while the current one is multiplied out of
+    // shared memory with packed FMAs; a diagonal slab (always the case for d <= 128) keeps a single copy.
+    __shared__ __align__(16) float sa[GRAM_TR][128 + 4];
+    __shared__ __align__(16) float sb[GRAM_TR][128 + 4];
     const int si = blockIdx.y / nslab, sj = blockIdx.y % nslab;
     const int i0 = si * 128, j0 = sj * 128;
+    const bool diag = si == sj;
+    const float(*pb)[128 + 4] = diag ? sa : sb;
     const int tid = threadIdx.x;
     const int ti = tid >> 4, tj = tid & 15;  // 16 x 16 threads, 8x8 outputs each
-    float acc[8][8];
+    const bool vec_ok = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(F) & 15) == 0;
+    float2 acc[8][4];
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = 0.f;
-    const int64_t ntiles = (rows + GRAM_TR - 1) / GRAM_TR;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t r0 = tile * GRAM_TR;
-        __syncthreads();
-        for (int e = tid; e < GRAM_TR * 128; e += GRAM_THREADS) {
-            const int r = e >> 7, c = e & 127;
-            const int64_t gr = r0 + r;
-            float va = 0.f, vb = 0.f;
+        for (int v = 0; v < 4; ++v) acc[u][v] = make_float2(0.f, 0.f);
+    // thread's four 128-bit pieces of a 32 x 128 tile: piece k = row (tid >> 5) + 8k, columns 4 * (tid & 31)
+    const int lr = tid >> 5, lc = (tid & 31) * 4;
+    auto fetch = [&](int64_t r0, int c0, float4(&v)[4]) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t gr = r0 + lr + 8 * k;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gr < rows) {
-                if (i0 + c < D) va = __ldg(F + gr * ld + i0 + c);
-                if (j0 + c < D) vb = __ldg(F + gr * ld + j0 + c);
+                const float* src = F + gr * ld + c0 + lc;
+                if (vec_ok && c0 + lc + 3 < D) {
+                    x = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (c0 + lc + 0 < D) x.x = __ldg(src + 0);
+                    if (c0 + lc + 1 < D) x.y = __ldg(src + 1);
+                    if (c0 + lc + 2 < D) x.z = __ldg(src + 2);
+                    if (c0 + lc + 3 < D) x.w = __ldg(src + 3);
+                }
             }
-            sa[r][c] = va;
-            sb[r][c] = vb;
+            v[k] = x;
+        }
+    };
+    const int64_t ntiles = (rows + GRAM_TR - 1) / GRAM_TR;
+    float4 va[4], vb[4];
+    if ((int64_t)blockIdx.x < ntiles) {
+        fetch((int64_t)blockIdx.x * GRAM_TR, i0, va);
+        if (!diag) fetch((int64_t)blockIdx.x * GRAM_TR, j0, vb);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            *reinterpret_cast<float4*>(&sa[lr + 8 * k][lc]) = va[k];
+            if (!diag) *reinterpret_cast<float4*>(&sb[lr + 8 * k][lc]) = vb[k];
         }
         __syncthreads();
+        if (tile + gridDim.x < ntiles) {
+            fetch((tile + gridDim.x) * GRAM_TR, i0, va);
+            if (!diag) fetch((tile + gridDim.x) * GRAM_TR, j0, vb);
+        }
 #pragma unroll 4
         for (int r = 0; r < GRAM_TR; ++r) {
-            float av[8], bv[8];
             const float4 a0 = *reinterpret_cast<const float4*>(&sa[r][ti * 8]);
             const float4 a1 = *reinterpret_cast<const float4*>(&sa[r][ti * 8 + 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&sb[r][tj * 8]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&sb[r][tj * 8 + 4]);
-            av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w;
-            av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
-            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-            bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            const float4 b0 = *reinterpret_cast<const float4*>(&pb[r][tj * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&pb[r][tj * 8 + 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int v = 0; v < 8; ++v) acc[u][v] += av[u] * bv[v];
+                for (int v = 0; v < 4; ++v) acc[u][v] = gram_ffma2(make_float2(av[u], av[u]), bv[v], acc[u][v]);
         }
     }
     float* out = partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 128 * 128;
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-        for (int v = 0; v < 8; ++v) out[(ti * 8 + u) * 128 + tj * 8 + v] = acc[u][v];
+        for (int v = 0; v < 4; ++v)
+            *reinterpret_cast<float2*>(out + (ti * 8 + u) * 128 + tj * 8 + 2 * v) = acc[u][v];
 }
 
 __global__ void gram_reduce_kernel(const float* __restrict__ partial, int nparts, int nslab, int D,
