@@ -311,8 +311,14 @@ def main():
     alg_bytes = [algorithmic_bytes(my_nnz[a], my_rows[a], d) for a in (0, 1)]
     t_solve = sum(np.mean(per_axis_ms[a]) for a in (0, 1)) / 1e3
     achieved = sum(alg_bytes) / t_solve / 1e9
+    # DRAM traffic of the same launches from the committed ncu capture (profiles/run_ncu.sh); single-GPU C2 only
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_c2.json")
+    if world == 1 and args.workload == "c2" and os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["user_pass"] + tj["item_pass"], tj["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "ALS row-solve (user + item launches of one iteration)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ALS row-solve (user + item launches of one iteration)",
                 "algorithmic_bytes_per_launch": {"user_pass": alg_bytes[0], "item_pass": alg_bytes[1]},
                 "launch_ms": {"user_pass": float(np.mean(per_axis_ms[0])), "item_pass": float(np.mean(per_axis_ms[1]))},
                 "share_of_step": t_solve * 1e3 * args.steps / ms}

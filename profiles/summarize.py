@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Turns ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
 
-  python profiles/summarize.py launches gpurun_out/<tag>_launches_c2.csv  > profiles/<tag>_launches_c2.md
+  python profiles/summarize.py launches gpurun_out/<tag>_launches_c2.csv [profiles/traffic_c2.json] > profiles/<tag>_launches_c2.md
   python profiles/summarize.py full     gpurun_out/<tag>_prof.ncu-rep     > profiles/<tag>_prof_summary.md
 """
 import csv
@@ -11,26 +11,52 @@ import sys
 from collections import OrderedDict
 
 
-def launches(path):
+def launches(path, traffic_json=None):
+    """Per-kernel totals of an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum]`
+    launch list; with DRAM metrics also the per-iteration DRAM traffic of the ALS solve launches (last iteration)."""
     rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("==")]
     hdr = rows[0]
-    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
-    agg = OrderedDict()
+    ik, im, iv, iu, iid = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
+    per = OrderedDict()
     for r in rows[1:]:
         v = float(r[iv].replace(",", ""))
-        v = v / 1e6 if r[iu] in ("nsecond", "ns") else (v / 1e3 if r[iu] in ("usecond", "us") else v)  # -> ms
+        if r[im] == "gpu__time_duration.sum":
+            v = v / 1e6 if r[iu] in ("nsecond", "ns") else (v / 1e3 if r[iu] in ("usecond", "us") else v)  # -> ms
+        else:
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(r[iu], 1.0)
         name = r[ik].split("(")[0].replace("void ", "").replace("bfl::", "")
-        ours_prefixes = ("als_", "gram_", "fast_", "bpr_", "warp_", "sgd_", "probe_")
-        name = name if name.startswith(ours_prefixes) else "torch (workload generation)"
-        a = agg.setdefault(name, [0, 0.0])
+        per.setdefault(r[iid], {"name": name})[r[im]] = v
+    ours_prefixes = ("als_", "gram_", "fast_", "bpr_", "warp_", "sgd_", "probe_")
+    agg = OrderedDict()
+    for d in per.values():
+        name = d["name"] if d["name"].startswith(ours_prefixes) else "torch (workload generation)"
+        a = agg.setdefault(name, [0, 0.0, 0.0])
         a[0] += 1
-        a[1] += v
-    tot = sum(v for _, v in agg.values())
-    ours = sum(v for k, (_, v) in agg.items() if "torch" not in k)
-    print("| kernel | launches | total ms | share of our kernels |\n|---|---|---|---|")
-    for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("| `%s` | %d | %.2f | %s |" % (k, n, v, "%.1f %%" % (100 * v / ours) if "torch" not in k else "-"))
+        a[1] += d.get("gpu__time_duration.sum", 0.0)
+        a[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+    tot = sum(v[1] for v in agg.values())
+    ours = sum(v[1] for k, v in agg.items() if "torch" not in k)
+    print("| kernel | launches | total ms | share of our kernels | DRAM GB (rd+wr) |\n|---|---|---|---|---|")
+    for k, (n, v, b) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("| `%s` | %d | %.2f | %s | %.1f |" % (k, n, v, "%.1f %%" % (100 * v / ours) if "torch" not in k else "-", b / 1e9))
     print("\ntotal %.1f ms, ours %.1f ms (ncu: cold-cache, serialised launches -- compare shares, not absolutes)" % (tot, ours))
+    # last iteration: the solve launches after the last two Gram reductions (user side, then item side)
+    seq = list(per.values())
+    gi = [i for i, d in enumerate(seq) if d["name"].startswith("gram_reduce")]
+    if len(gi) >= 2 and "dram__bytes_read.sum" in seq[gi[-1]]:
+        def solve(lo, hi):
+            ds = [d for d in seq[lo:hi] if d["name"].startswith("als_")]
+            return (sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in ds),
+                    sum(d["gpu__time_duration.sum"] for d in ds), len(ds))
+        ub, ut, un = solve(gi[-2], gi[-1])
+        ib, it, inn = solve(gi[-1], len(seq))
+        print("\nlast iteration: user-side solve %d launches %.1f ms %.1f GB DRAM; item-side solve %d launches %.1f ms %.1f GB DRAM"
+              % (un, ut, ub / 1e9, inn, it, ib / 1e9))
+        if traffic_json:
+            import json
+            json.dump({"user_pass": ub, "item_pass": ib, "unit": "byte",
+                       "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, last iteration of `%s`" % path},
+                      open(traffic_json, "w"), indent=1)
 
 
 METRICS = [("gpu__time_duration.sum", "ms"), ("dram__bytes_read.sum", "GB rd"), ("dram__bytes_write.sum", "GB wr"),
@@ -67,4 +93,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+    else:
+        full(sys.argv[2])
