@@ -253,7 +253,7 @@ def main():
     # contiguous row shards per rank + one in-place all-gather per half-epoch (buffalo_b200/parallel/dist.py)
     from buffalo_b200.parallel.dist import ShardedALS
     drv = ShardedALS(obj.precompute_device, obj.update_device, P, Q, rank, world, dist if world > 1 else None,
-                     exchange=args.exchange, backend=obj)
+                     exchange=args.exchange, backend=obj, indptrs=(wl["r_indptr"], wl["c_indptr"]))
     (u0, u1, _), (i0, i1, _) = drv.ranges
     stream = torch.cuda.current_stream()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731

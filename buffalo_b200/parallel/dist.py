@@ -3,6 +3,7 @@ per rank, full factor replicas everywhere, ONE exchange step per half-epoch -- a
 freshly updated factor shard over NCCL (NVLink 5 / NVSwitch).  The same class drives the gloo CPU tests
 (tests/test_dist_cpu.py) with a CPU row-update function, so the sharding / exchange logic is covered without GPUs.
 """
+import numpy as np
 
 
 def row_shard(total, rank, world):
@@ -10,6 +11,31 @@ def row_shard(total, rank, world):
     per = (total + world - 1) // world
     lo = min(rank * per, total)
     return lo, min(lo + per, total), per
+
+
+def nnz_shard(indptr_end, rank, world):
+    """Contiguous row range of `rank` when rows are split so that every rank gets (nearly) the same number of
+    nonzeros: boundary k is the first row whose end offset reaches k * nnz / world (prefix-sum split of
+    indptr).  `indptr_end` = exclusive end offsets (NumPy array or torch tensor).  Needs an exchange that accepts
+    unequal shard sizes (the fused p2p exchange does; the in-place all-gather does not)."""
+    n = int(indptr_end.shape[0])
+    if n == 0:
+        return 0, 0, None
+    nnz = int(indptr_end[-1])
+
+    def boundary(k):
+        if k <= 0:
+            return 0
+        if k >= world:
+            return n
+        target = (nnz * k + world - 1) // world
+        if hasattr(indptr_end, "cpu"):   # torch tensor (possibly on the device)
+            import torch
+            t = torch.tensor([target], dtype=indptr_end.dtype, device=indptr_end.device)
+            return int(torch.searchsorted(indptr_end, t, right=False).item()) + 1 if target > 0 else 0
+        return int(np.searchsorted(indptr_end, target, side="left")) + 1 if target > 0 else 0
+    lo, hi = min(boundary(rank), n), min(boundary(rank + 1), n)
+    return lo, max(lo, hi), None
 
 
 _opened = {}   # IPC handle bytes -> mapped base address (a handle may be opened once per process)
@@ -84,12 +110,18 @@ class ShardedALS(object):
     (backend.set_peer_replicas), so the transfer overlaps the solve row by row over NVLink; the only collective
     left is a one-element all-reduce used as a stream-ordered barrier between half-epochs."""
 
-    def __init__(self, precompute, update, P, Q, rank=0, world=1, dist=None, exchange="allgather", backend=None):
+    def __init__(self, precompute, update, P, Q, rank=0, world=1, dist=None, exchange="allgather", backend=None,
+                 indptrs=None):
+        """indptrs = (rowwise end offsets, colwise end offsets): with the p2p exchange the rows are then split by
+        nonzeros instead of by count (skewed matrices: equal row counts can mean very unequal work)."""
         self.precompute, self.update, self.P, self.Q = precompute, update, P, Q
         self.rank, self.world, self.dist = rank, world, dist
         self.mode = exchange if world > 1 else "none"
-        self.ranges = [row_shard(P.shape[0], rank, world), row_shard(Q.shape[0], rank, world)]
-        if world > 1:
+        if self.mode == "p2p" and indptrs is not None:
+            self.ranges = [nnz_shard(indptrs[0], rank, world), nnz_shard(indptrs[1], rank, world)]
+        else:
+            self.ranges = [row_shard(P.shape[0], rank, world), row_shard(Q.shape[0], rank, world)]
+        if self.mode == "allgather":
             for F in (P, Q):
                 assert F.shape[0] % world == 0, "row counts must be divisible by the world size (pad the matrix)"
         if self.mode == "p2p":

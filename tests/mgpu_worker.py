@@ -28,7 +28,7 @@ def run(world, rank, mode, P0, Q0, rw, cw, dev, d):
     obj.bind_csr(0, t(rw[0]), t(rw[1]), t(rw[2]))
     obj.bind_csr(1, t(cw[0]), t(cw[1]), t(cw[2]))
     drv = ShardedALS(obj.precompute_device, obj.update_device, P, Q, rank, world, dist if world > 1 else None,
-                     exchange=mode, backend=obj)
+                     exchange=mode, backend=obj, indptrs=(rw[0], cw[0]))   # p2p: rows split by nonzeros
     for _ in range(2):
         drv.iteration()
     torch.cuda.synchronize()

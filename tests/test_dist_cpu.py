@@ -71,3 +71,24 @@ def test_row_shard():
     from buffalo_b200.parallel.dist import row_shard
     assert [row_shard(10, r, 4)[:2] for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert row_shard(8, 1, 2) == (4, 8, 4) and row_shard(3, 3, 4)[:2] == (3, 3)
+
+
+def test_nnz_shard_covers_rows_and_balances_nonzeros():
+    """rows are split by a prefix sum of nonzeros (used with the fused p2p exchange)."""
+    from buffalo_b200.parallel.dist import nnz_shard
+    rng = np.random.default_rng(0)
+    deg = np.minimum(rng.zipf(1.3, 5000), 4000)            # heavily skewed row lengths
+    deg[:7] = 0
+    ind = np.cumsum(deg).astype(np.int64)
+    for world in (1, 2, 3, 8):
+        parts = [nnz_shard(ind, r, world) for r in range(world)]
+        assert parts[0][0] == 0 and parts[-1][1] == len(ind)
+        assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))        # contiguous, disjoint, complete
+        per = [int(ind[hi - 1] - (ind[lo - 1] if lo else 0)) if hi > lo else 0 for lo, hi, _ in parts]
+        assert sum(per) == int(ind[-1])
+        assert max(per) <= int(ind[-1]) / world + deg.max()                         # within one row of the ideal
+        tparts = [nnz_shard(torch.from_numpy(ind), r, world) for r in range(world)]
+        assert [p[:2] for p in tparts] == [p[:2] for p in parts]
+    assert nnz_shard(np.zeros(0, np.int64), 0, 2)[:2] == (0, 0)
+    empty = [nnz_shard(np.zeros(5, np.int64), r, 2)[:2] for r in range(2)]          # all-empty matrix: still a cover
+    assert empty[0][0] == 0 and empty[0][1] == empty[1][0] and empty[1][1] == 5
