@@ -29,6 +29,8 @@ WORKLOADS = {
                desc="ALS d=128 10Mx1M 1B-nnz synthetic CSR (BASELINE configs[1])"),
     "c2_small": dict(users=1_000_000, items=100_000, nnz=100_000_000, d=128,
                      desc="1/10-scale C2 (debug only; NOT the headline workload)"),
+    "c5_small": dict(users=500_000, items=50_000, nnz=200_000_000, d=256,
+                     desc="1/10-scale, uniform-item stand-in for BASELINE configs[4] (d=256; debug only)"),
     "tiny": dict(users=20_000, items=5_000, nnz=1_000_000, d=128, desc="smoke-scale (debug only)"),
 }
 ALS_OPT = dict(d=128, optimizer="manual_cg", num_workers=1, compute_loss_on_training=False, alpha=8.0, reg_u=0.1,

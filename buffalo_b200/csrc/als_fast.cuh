@@ -555,7 +555,8 @@ struct FastCache {
 };
 
 inline bool fast_als_applicable(int optimizer_code, int d, int vdim, int block_size) {
-    return optimizer_code == 8 && d % 32 == 0 && d <= 128 && vdim == d && block_size == 32;
+    // d <= 128: the Gram matrix lives in shared memory; 128 < d <= 256: it is read through L1/L2 (GSM = false)
+    return optimizer_code == 8 && d % 32 == 0 && d <= 256 && vdim == d && block_size == 32;
 }
 
 template <int W, int K, int KS, bool RES, bool GSM>
@@ -619,19 +620,26 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         a.row_end = fb->offset[c + 1];
         const FastClass fc = fast_class(c);
         int rc = BFL_OK;
-        if (use_mma && mma_class_covered(c)) {
+        if (use_mma && a.D <= 128 && mma_class_covered(c)) {
             rc = mma_launch(c, a, fc.cap, num_sms, st);
             if (rc != BFL_OK) return rc;
             continue;
         }
+        const bool gsm = a.D <= 128;   // d x (d+4) floats of Gram fit next to the staging buffers only up to d = 128
         switch (c) {
-            case 0: rc = fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 1: rc = fast_launch_class<1, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 2: rc = fast_launch_class<2, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 3: rc = fast_launch_class<4, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
-            case 4: rc = fast_launch_class<8, 2, 0, true, true>(a, fc.cap, num_sms, st); break;
+            case 0: rc = gsm ? fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<1, 1, 0, true, false>(a, fc.cap, num_sms, st); break;
+            case 1: rc = gsm ? fast_launch_class<1, 2, 0, true, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<1, 2, 0, true, false>(a, fc.cap, num_sms, st); break;
+            case 2: rc = gsm ? fast_launch_class<2, 2, 0, true, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<2, 2, 0, true, false>(a, fc.cap, num_sms, st); break;
+            case 3: rc = gsm ? fast_launch_class<4, 2, 0, true, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<4, 2, 0, true, false>(a, fc.cap, num_sms, st); break;
+            case 4: rc = gsm ? fast_launch_class<8, 2, 0, true, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<8, 2, 0, true, false>(a, fc.cap, num_sms, st); break;
             case 5: rc = fast_launch_class<16, 2, 1, true, false>(a, fc.cap, num_sms, st); break;
-            case 6: rc = fast_launch_class<16, 1, 0, false, true>(a, fc.cap, num_sms, st); break;
+            case 6: rc = gsm ? fast_launch_class<16, 1, 0, false, true>(a, fc.cap, num_sms, st)
+                             : fast_launch_class<16, 1, 0, false, false>(a, fc.cap, num_sms, st); break;
         }
         if (rc != BFL_OK) return rc;
     }

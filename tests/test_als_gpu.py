@@ -135,7 +135,7 @@ def test_c1_config_training_trajectory(cuda_lib):
         assert abs(rmse_g - rmse_o) < 1e-4 * rmse_o
 
 
-@pytest.mark.parametrize("d", [128, 64, 32])
+@pytest.mark.parametrize("d", [128, 64, 32, 96, 256])
 def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
     """The tuned iALS++ kernels bin rows by length (<=32, 64, 128, 256, 512 register-resident; <=1536 two register
     tiles + one shared-memory tile per warp, SIMT kernel by default, tensor-core Gram variant with
