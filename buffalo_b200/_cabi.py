@@ -71,6 +71,7 @@ PROTOTYPES = {
     "bfl_sgd_apply_triples_device": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _vp]),
     "bfl_sgd_sample_device": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "bfl_sgd_grad_device": (_vp, [_vp, C.c_int]),
+    "bfl_sgd_count_device": (_vp, [_vp, C.c_int]),
     "bfl_sgd_set_trace_device": (C.c_int, [_vp, _vp, _vp]),
     "bfl_sgd_epoch": (C.c_int, [_vp]),
     "bfl_sgd_current_lr": (_d, [_vp]),

@@ -264,6 +264,17 @@ class CuSGD(object):
             __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
         return torch.as_tensor(_Arr(), device="cuda").view(*shape)
 
+    def count_tensor(self, which, rows):
+        """int32[rows] sample counters of per_coordinate_normalize (0: P rows, 1: Q rows); None if not allocated."""
+        import torch
+        ptr = self._lib.bfl_sgd_count_device(self._h, int(which))
+        if not ptr:
+            return None
+
+        class _Arr(object):
+            __cuda_array_interface__ = {"shape": (int(rows),), "typestr": "<i4", "data": (ptr, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
+
     def set_trace(self, trials, negs):
         self._keep += [trials, negs]
         _cabi.check(self._lib.bfl_sgd_set_trace_device(self._h, _dev(trials, "int32", "trials"),

@@ -888,6 +888,11 @@ float* bfl_sgd_grad_device(bfl_sgd_t* h, int which) {
     return which == 0 ? h->gP.p : (which == 1 ? h->gQ.p : h->gQb.p);
 }
 
+int32_t* bfl_sgd_count_device(bfl_sgd_t* h, int which) {
+    if (!h) return nullptr;
+    return which == 0 ? h->cP.p : h->cQ.p;
+}
+
 int bfl_sgd_set_trace_device(bfl_sgd_t* h, int32_t* d_trials, int32_t* d_negs) {
     if (!h) BFL_FAIL(BFL_ERR_ARG, "null handle");
     h->trace_trials = d_trials;

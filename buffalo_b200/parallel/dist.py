@@ -157,3 +157,67 @@ class ShardedALS(object):
     def iteration(self, on_update=None):
         self.half_epoch(0, on_update)
         self.half_epoch(1, on_update)
+
+
+class ShardedSGD(object):
+    """Row-sharded BPRMF / WARP epoch: every rank owns a contiguous, nnz-balanced user range of the
+    rowwise CSR and holds full replicas of P, Q (and Qb).
+
+    * gradient-accumulating configurations (WARP always; BPR with adagrad / adam; bpr.cc:138-156, warp.cc:156-158):
+      P and Q are read-only inside an epoch and the gradient sums are additive over users, so the ranks all-reduce
+      the accumulators (and the per-row sample counters) and then apply the SAME optimizer step
+      (`update_parameters`) -- the replicas stay identical and the result equals the single-GPU epoch up to fp32
+      summation order.  Negative sampling is keyed by the global positive index, so the draws do not depend on the
+      number of ranks.  The reference does not zero the accumulators after the step (algo.cc:382-465): only rank 0
+      carries that leftover into the next epoch, so the all-reduce counts it once.
+    * plain-SGD BPR (Hogwild, bpr.cc:157-171): each rank applies its users' updates to its replicas; after the
+      epoch the item-side deltas are summed over ranks (Q = Q_start + sum of deltas: bounded staleness of one
+      epoch) and each user range is broadcast from its owner.
+
+    `accumulate(lo, hi)` runs the local part of the epoch, `apply()` the optimizer step; `grads` is the list of
+    tensors to all-reduce in accumulate mode (float or int), `P, Q, Qb` the replicas."""
+
+    def __init__(self, accumulate, apply, P, Q, Qb, indptr_end, rank=0, world=1, dist=None, grads=None):
+        self.accumulate, self.apply = accumulate, apply
+        self.P, self.Q, self.Qb = P, Q, Qb
+        self.rank, self.world, self.dist = rank, world, dist
+        self.grads = [g for g in (grads or []) if g is not None]
+        self.mode = "accumulate" if self.grads else "sgd"
+        self.bounds = [nnz_shard(indptr_end, r, world)[0] for r in range(world)] + [int(indptr_end.shape[0])]
+        self.lo, self.hi = self.bounds[rank], self.bounds[rank + 1]
+
+    def local_positives(self, indptr_end):
+        if self.hi <= self.lo:
+            return 0
+        return int(indptr_end[self.hi - 1]) - (int(indptr_end[self.lo - 1]) if self.lo else 0)
+
+    def epoch(self):
+        if self.world == 1:
+            self.accumulate(self.lo, self.hi)
+            self.apply()
+            return
+        if self.mode == "accumulate":
+            if self.rank != 0:
+                for g in self.grads:
+                    if g.is_floating_point():
+                        g.zero_()
+            self.accumulate(self.lo, self.hi)
+            for g in self.grads:
+                self.dist.all_reduce(g)
+            self.apply()
+            return
+        q0 = self.Q.clone()
+        b0 = self.Qb.clone() if self.Qb is not None else None
+        self.accumulate(self.lo, self.hi)
+        dq = self.Q - q0
+        self.dist.all_reduce(dq)
+        self.Q.copy_(q0.add_(dq))
+        if b0 is not None:
+            db = self.Qb - b0
+            self.dist.all_reduce(db)
+            self.Qb.copy_(b0.add_(db))
+        for r in range(self.world):
+            lo, hi = self.bounds[r], self.bounds[r + 1]
+            if hi > lo:
+                self.dist.broadcast(self.P[lo:hi], src=r)
+        self.apply()

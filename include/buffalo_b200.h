@@ -201,6 +201,10 @@ int bfl_sgd_sample_device(bfl_sgd_t* h, int64_t row_begin, int64_t row_end, int3
                           int32_t* d_pos, int32_t* d_neg, void* stream);
 /* device pointers of the gradient accumulators (NULL for optimizer == sgd) */
 float* bfl_sgd_grad_device(bfl_sgd_t* h, int which /*0 P, 1 Q, 2 Qb*/);
+/* device pointers of the per-row sample counters used by per_coordinate_normalize (algo.cc:398-413; int32[rows]).
+ * Together with the gradient accumulators these are what a row-sharded multi-GPU epoch all-reduces before
+ * update_parameters. */
+int32_t* bfl_sgd_count_device(bfl_sgd_t* h, int which /*0 P rows, 1 Q rows*/);
 /* WARP: per-positive trial counts / chosen negatives of the last add_jobs (device int32[nnz]) */
 int bfl_sgd_set_trace_device(bfl_sgd_t* h, int32_t* d_trials, int32_t* d_negs);
 /* current epoch counter / decayed learning rate (algo.cc:284-287) */

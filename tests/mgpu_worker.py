@@ -37,6 +37,44 @@ def run(world, rank, mode, P0, Q0, rw, cw, dev, d):
     return P.cpu().numpy(), Q.cpu().numpy()
 
 
+def run_sgd(world, rank, kind, optimizer, P0, Q0, indptr, keys, dev, d):
+    """3 epochs of BPRMF / WARP through ShardedSGD; returns the factors (device replicas are identical by design)."""
+    from buffalo_b200.parallel.dist import ShardedSGD
+    U, I = P0.shape[0], Q0.shape[0]
+    opt = dict(d=d, num_workers=1, optimizer=optimizer, use_bias=(kind == "bpr"), update_i=True, update_j=True,
+               reg_u=0.02, reg_i=0.02, reg_j=0.02, reg_b=0.02, lr=0.05, min_lr=0.0001, beta1=0.9, beta2=0.999,
+               per_coordinate_normalize=(optimizer == "adam"), num_negative_samples=2, sampling_power=0.0,
+               verify_neg=True, random_seed=3, num_iters=3, compute_loss_on_training=True, max_trials=30,
+               threshold=1.0, score_func="dot")
+    g = backend.CuSGD(kind)
+    assert g.init(opt)
+    P, Q = torch.from_numpy(P0.copy()).to(dev), torch.from_numpy(Q0.copy()).to(dev)
+    Qb = torch.zeros(I, 1, device=dev)
+    t_ind, t_keys = torch.from_numpy(indptr).to(dev), torch.from_numpy(keys).to(dev)
+    grads = None
+    drv = ShardedSGD(None, None, P, Q, Qb, indptr, rank, world, dist if world > 1 else None)
+    g.bind_factors(P, Q, Qb, drv.local_positives(indptr))
+    g.bind_csr(t_ind, t_keys)
+    g.launch_workers()
+    if optimizer != "sgd":
+        grads = [g.grad_tensor(0, P.shape), g.grad_tensor(1, Q.shape)] + ([g.grad_tensor(2, (I,))] if kind == "bpr" else [])
+        grads += [g.count_tensor(0, U), g.count_tensor(1, I)]
+    drv = ShardedSGD(g.add_jobs_device, g.update_parameters_device, P, Q, Qb, indptr, rank, world,
+                     dist if world > 1 else None, grads=grads)
+    for _ in range(3):
+        drv.epoch()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    rng = np.random.default_rng(11)     # probe triples (observed positive vs random item), same on every rank
+    beg = np.concatenate([[0], indptr[:-1]])
+    us = rng.choice(np.nonzero(indptr > beg)[0], 500).astype(np.int32)
+    ps = np.array([keys[rng.integers(beg[u], indptr[u])] for u in us], np.int32)
+    ns = rng.integers(0, I, 500).astype(np.int32)
+    loss = g.compute_loss(us, ps, ns)
+    return P.cpu().numpy(), Q.cpu().numpy(), g.current_lr(), loss
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -53,6 +91,19 @@ def main():
         err = max(np.abs(P - ref[0]).max() / np.abs(ref[0]).max(), np.abs(Q - ref[1]).max() / np.abs(ref[1]).max())
         good = err < 1e-5      # same kernels, same inputs: only the loss-free row order differs
         print("rank %d mode %s rel err vs single GPU %.2e %s" % (rank, mode, err, "OK" if good else "FAIL"), flush=True)
+        ok = ok and good
+    # BPRMF / WARP: gradient-accumulating configurations must equal the single-GPU epochs; plain-SGD BPR is
+    # Hogwild with one item-delta exchange per epoch (close to, not equal to, the single-GPU run)
+    Ps, Qs = init_factors(U, 64, 64, 5, 0.2, True), init_factors(I, 64, 64, 6, 0.2, True)
+    for kind, optimizer, tol in (("warp", "adagrad", 2e-4), ("bpr", "adam", 2e-4), ("bpr", "sgd", 0.4)):
+        ref = run_sgd(1, 0, kind, optimizer, Ps, Qs, indptr, keys, dev, 64)
+        got = run_sgd(world, rank, kind, optimizer, Ps, Qs, indptr, keys, dev, 64)
+        err = max(np.linalg.norm(got[0] - ref[0]) / np.linalg.norm(ref[0]), np.linalg.norm(got[1] - ref[1]) / np.linalg.norm(ref[1]))
+        moved = np.linalg.norm(got[1] - Qs) / np.linalg.norm(Qs)
+        good = err < tol and moved > 1e-3 and abs(got[2] - ref[2]) < 1e-9 and np.isfinite(got[0]).all()
+        good = good and abs(got[3] - ref[3]) < 0.15 * abs(ref[3]) + 1e-6      # same probe loss level
+        print("rank %d %s/%s rel err vs single GPU %.2e (moved %.2e) probe loss %.4f vs %.4f %s"
+              % (rank, kind, optimizer, err, moved, got[3], ref[3], "OK" if good else "FAIL"), flush=True)
         ok = ok and good
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
