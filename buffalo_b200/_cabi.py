@@ -44,6 +44,7 @@ PROTOTYPES = {
     "bfl_als_bind_factors_device": (C.c_int, [_vp, _vp, _i64, _vp, _i64]),
     "bfl_als_bind_csr_device": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, _i64]),
     "bfl_als_precompute_device": (C.c_int, [_vp, C.c_int, _vp]),
+    "bfl_als_precompute_rows_device": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp]),
     "bfl_als_update_device": (C.c_int, [_vp, C.c_int, _i64, _i64, _vp, _vp]),
     "bfl_als_set_peer_replicas": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "bfl_als_gram_device": (_vp, [_vp]),

@@ -122,6 +122,11 @@ class CuALS(object):
     def precompute_device(self, axis, stream=None):
         _cabi.check(self._lib.bfl_als_precompute_device(self._h, int(axis), _stream_ptr(stream)), "precompute_device")
 
+    def precompute_rows_device(self, axis, row_begin, row_end, stream=None):
+        """Partial Gram over rows [row_begin,row_end) of the opposite factor (to be all-reduced via gram_tensor())."""
+        _cabi.check(self._lib.bfl_als_precompute_rows_device(self._h, int(axis), int(row_begin), int(row_end),
+                                                             _stream_ptr(stream)), "precompute_rows_device")
+
     def update_device(self, axis, row_begin, row_end, loss=None, stream=None):
         """loss: optional torch float64 CUDA tensor[2] receiving (+=) numerator, denominator."""
         lp = _dev(loss, "float64", "loss") if loss is not None else None

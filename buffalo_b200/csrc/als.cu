@@ -393,6 +393,19 @@ int bfl_als_precompute_device(bfl_als_t* h, int axis, void* stream) {
     return gram(h, F, rows, (cudaStream_t)stream);
 }
 
+int bfl_als_precompute_rows_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end, void* stream) {
+    if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "factors not bound");
+    if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
+    const float* F = axis == 0 ? h->dQ : h->dP;
+    const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
+    if (row_begin < 0 || row_end > rows || row_end < row_begin) BFL_FAIL(BFL_ERR_ARG, "bad row range");
+    if (row_end == row_begin) {
+        BFL_CUDA(cudaMemsetAsync(h->G.p, 0, sizeof(float) * (size_t)h->d * h->d, (cudaStream_t)stream));
+        return BFL_OK;
+    }
+    return gram(h, F + (size_t)row_begin * h->vdim, row_end - row_begin, (cudaStream_t)stream);
+}
+
 int bfl_als_update_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end, double* d_loss,
                           void* stream) {
     if (!h || !h->factors_ready) BFL_FAIL(BFL_ERR_STATE, "factors not bound");

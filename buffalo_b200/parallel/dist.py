@@ -124,6 +124,10 @@ class ShardedALS(object):
         if self.mode == "allgather":
             for F in (P, Q):
                 assert F.shape[0] % world == 0, "row counts must be divisible by the world size (pad the matrix)"
+        # Gram of the opposite factor: every rank sums over its OWN row range and the d x d partials are all-reduced
+        # (instead of every rank re-reading the whole replica) when the backend offers the range form
+        self.backend = backend
+        self.sharded_gram = world > 1 and backend is not None and hasattr(backend, "precompute_rows_device")
         if self.mode == "p2p":
             import torch
             self._flag = torch.zeros(1, device=P.device)
@@ -146,7 +150,12 @@ class ShardedALS(object):
 
     def half_epoch(self, axis, on_update=None):
         lo, hi, _ = self.ranges[axis]
-        self.precompute(axis)
+        if self.sharded_gram:
+            olo, ohi, _ = self.ranges[1 - axis]     # the rows of the opposite factor this rank solved last
+            self.backend.precompute_rows_device(axis, olo, ohi)
+            self.dist.all_reduce(self.backend.gram_tensor())
+        else:
+            self.precompute(axis)
         if on_update:
             on_update(axis, "begin")
         self.update(axis, lo, hi)

@@ -113,6 +113,10 @@ int bfl_als_bind_csr_device(bfl_als_t* h, int axis, const int64_t* d_indptr, con
                             const float* d_vals, int64_t rows, int64_t nnz);
 /* FF = Y^T Y on `stream` */
 int bfl_als_precompute_device(bfl_als_t* h, int axis, void* stream);
+/* partial FF over rows [row_begin,row_end) of the opposite factor (axis 0: rows of Q) -- a row-sharded run computes
+ * the Gram of its own freshly solved rows and all-reduces the d x d result (bfl_als_gram_device_mut) instead of every
+ * rank recomputing the full matrix (als.cc:86-93 restricted to a row range). */
+int bfl_als_precompute_rows_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end, void* stream);
 /* solve rows [row_begin, row_end) of the bound CSR `axis` on `stream`; adds the loss pieces
  * into d_loss[0] (numerator), d_loss[1] (denominator) (device doubles, may be NULL). */
 int bfl_als_update_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end,

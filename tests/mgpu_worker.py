@@ -89,7 +89,9 @@ def main():
     for mode in ("allgather", "p2p"):
         P, Q = run(world, rank, mode, P0, Q0, (indptr, keys, vals), cw, dev, d)
         err = max(np.abs(P - ref[0]).max() / np.abs(ref[0]).max(), np.abs(Q - ref[1]).max() / np.abs(ref[1]).max())
-        good = err < 1e-5      # same kernels, same inputs: only the loss-free row order differs
+        # same kernels, same inputs; the Gram matrix is summed per rank and all-reduced, so its fp32 summation order
+        # differs from the single-GPU run (observed 1e-5 after two iterations; the parity bar is 1e-3)
+        good = err < 1e-4
         print("rank %d mode %s rel err vs single GPU %.2e %s" % (rank, mode, err, "OK" if good else "FAIL"), flush=True)
         ok = ok and good
     # BPRMF / WARP: gradient-accumulating configurations must equal the single-GPU epochs; plain-SGD BPR is
