@@ -1,22 +1,24 @@
 // Tuned iALS++ row-solve kernel for sm_100a (the d >= 128 path, lib/algo_impl/als/als.cc:211-358, and any
-// d % 32 == 0 with block_size 32).
+// d % 32 == 0, d <= 256, with block_size 32).
 //
 // Work decomposition
 //   * rows are binned by length; a TEAM of W warps (W = 1..16) owns one row at a time, a CTA of 16 warps
 //     holds 16/W teams, the grid is persistent (one CTA per SM) and strides over the class's row list;
-//   * inside a warp the lane id splits as lane = a + 8*b: `a` (0..7) selects an nnz inside a tile of 32
+//   * inside a warp the lane id splits as lane = b + 4*a: `a` (0..7) selects an nnz inside a tile of 32
 //     gathered rows (slots a, a+8, a+16, a+24), `b` (0..3) selects 8 of the 32 columns of the current
-//     column block.  A lane therefore holds a 4 x 8 register patch of the tile and every per-nnz operation
-//     of the block solve (q.p dot, axpy into the block vector) is pure register FMA work:
+//     column block (the four b-lanes of a row are adjacent lanes, so a 128-bit gather touches few lines).  A
+//     lane therefore holds a 4 x 8 register patch of the tile and every per-nnz operation of the block solve
+//     (q.p dot, axpy into the block vector) is pure register FMA work (packed fma.rn.f32x2):
 //        - a dot product over the block's 32 columns finishes with 2 shuffles (over b),
 //        - a tile's contribution to a 32-vector finishes with a 7-shuffle transposed reduction (over a)
-//          that leaves column `lane` in lane `lane`;
-//   * the gathered opposite-factor segments (128 B per nnz and block) are read with two 128-bit loads per
-//     slot (one full 32 B sector per lane) straight into registers and stay there for the whole block
-//     (b, 3 CG steps, Yui update) when the row fits the team (n <= 32*W*K); longer rows re-gather per pass
-//     (L2 hits);
+//          that leaves column 8b + a in lane (a, b);
+//   * the Yui pass streams the gathered opposite-factor rows with two 128-bit loads per slot and block straight
+//     into registers; the block passes are fed by lane-private cp.async staging of the next block's 128-byte
+//     segments (L2 hits) and keep K tiles per warp in registers for the whole block (b, 3 CG steps, Yui update)
+//     when the row fits the team (n <= 32*W*K); the long-row class keeps a third tile in its staging cells and
+//     rows beyond that re-gather per pass;
 //   * the dense terms x.G[:,blk] and A p are expressed as extra "pseudo-nnz" tiles whose rows come from the
-//     Gram matrix held in shared memory, distributed over the team's warps;
+//     Gram matrix (in shared memory for d <= 128, through L1/L2 above), distributed over the team's warps;
 //   * per-row state (x, Yui, alpha*v, keys) lives in shared memory; every warp contributes its tiles' partial
 //     of a team-wide 32-vector, the team's first warp (the solver) adds the partials up, runs the CG scalar
 //     recurrences and publishes the next direction -- two named barriers per reduction, no replicated algebra
