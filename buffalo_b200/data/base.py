@@ -2,7 +2,8 @@
 (buffalo/data/base.py).  Layout contract kept bit-for-bit (base.py:187-192, fileio.hpp:330-378): per
 orientation `indptr` int64[rows] = exclusive END offsets, `key` int32[nnz] zero-based, `val` float32[nnz],
 rows sorted by (row, col) resp. (col, row), duplicates kept.  The reference's text -> temp files -> parallel
-sort -> HDF5 pipeline is replaced by in-memory NumPy (this ingest is a one-off, outside the hot path)."""
+sort -> HDF5 pipeline is replaced by an in-memory build: NumPy on the host, or one device radix sort (torch) when a
+GPU is present and the matrix is large."""
 import os
 
 import numpy as np
@@ -11,8 +12,39 @@ from buffalo_b200.data import prepro, store
 from buffalo_b200.misc import aux, log
 
 
-def csr_from_triples(major, minor, vals, num_major, stable_sort=True):
-    """(indptr_end, key, val) sorted by (major, minor) with a stable sort (fileio.hpp:330-341)."""
+DEVICE_SORT_MIN_NNZ = 1 << 20   # below this the host sort is faster than the PCIe round trip
+
+
+def _csr_from_triples_torch(major, minor, vals, num_major, stable_sort, device):
+    """The same ordering on a torch device: one stable sort of the combined (major, minor) key -- on a GPU this is
+    the radix sort the 1B-nnz ingest needs (the reference: text -> temp files -> parallel sort,
+    fileio.hpp:263-419).  Works on CPU tensors too (used by the tests to pin it against the NumPy path)."""
+    import torch
+    mj = torch.as_tensor(np.ascontiguousarray(major), device=device).to(torch.int64)
+    mn = torch.as_tensor(np.ascontiguousarray(minor), device=device).to(torch.int64)
+    if stable_sort:
+        span = int(mn.max().item()) + 1 if mn.numel() else 1
+        order = torch.sort(mj * span + mn, stable=True).indices
+    else:
+        order = torch.sort(mj, stable=True).indices
+    indptr = torch.cumsum(torch.bincount(mj, minlength=num_major), 0)
+    key = mn[order].to(torch.int32)
+    val = torch.as_tensor(np.ascontiguousarray(vals), device=device)[order].to(torch.float32)
+    return indptr.cpu().numpy().astype(np.int64), key.cpu().numpy(), val.cpu().numpy()
+
+
+def csr_from_triples(major, minor, vals, num_major, stable_sort=True, device=None):
+    """(indptr_end, key, val) sorted by (major, minor) with a stable sort (fileio.hpp:330-341).
+    device: None = the GPU when one is present and the matrix is large, else the host; or an explicit torch device."""
+    if device is None and len(major) >= DEVICE_SORT_MIN_NNZ:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                device = "cuda"
+        except ImportError:
+            pass
+    if device is not None:
+        return _csr_from_triples_torch(major, minor, vals, num_major, stable_sort, device)
     if stable_sort:
         order = np.lexsort((minor, major))
     else:  # keep the input order inside a row (Stream, internal_data_type="stream")

@@ -137,3 +137,21 @@ def test_sgd_trainers_quality(cuda_lib, ml100k_like, cls_name, kw):
         assert np.linalg.norm(algo.P, axis=1).max() <= 1.0 + 1e-4           # warp.cc:196-200
     assert len(algo.most_similar("item_10", 5)) == 5
     assert "train_loss" in ret and first == []
+
+
+def test_csr_ingest_sort_on_device(cuda_lib):
+    """the (row, col) ordering of the ingest on the GPU equals the host build."""
+    from buffalo_b200.data.base import csr_from_triples
+    rng = np.random.default_rng(4)
+    n, U, I = 3_000_000, 50_000, 20_000
+    rows = rng.integers(0, U, n).astype(np.int64)
+    cols = rng.integers(0, I, n).astype(np.int64)
+    vals = rng.integers(1, 6, n).astype(np.float32)
+    a = csr_from_triples(rows[:200000], cols[:200000], vals[:200000], U)              # < threshold: host path
+    b = csr_from_triples(rows[:200000], cols[:200000], vals[:200000], U, device="cuda")
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    c = csr_from_triples(rows, cols, vals, U)                                        # >= threshold: device path
+    assert c[0][-1] == n and np.all(np.diff(c[0]) >= 0)
+    beg = np.concatenate([[0], c[0][:-1]])
+    for r in (0, 17, U - 1):
+        assert np.all(np.diff(c[1][beg[r]:c[0][r]]) >= 0)

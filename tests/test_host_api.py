@@ -305,3 +305,20 @@ def test_package_surface():
     from buffalo.parallel import ParALS  # noqa: F401
     with pytest.raises(NotImplementedError):
         buffalo.W2V()
+
+
+def test_csr_from_triples_device_sort_matches_host_sort():
+    """The torch ordering (run here on CPU tensors; on a GPU box the same code runs on `cuda`) reproduces the NumPy
+    build of both orientations: sorted by (major, minor), duplicates kept in input order, end offsets."""
+    from buffalo_b200.data.base import csr_from_triples
+    rng = np.random.default_rng(3)
+    n, U, I = 20000, 300, 170
+    rows = rng.integers(0, U, n).astype(np.int64)
+    cols = rng.integers(0, I, n).astype(np.int64)
+    vals = rng.normal(size=n).astype(np.float32)
+    rows[:50], cols[:50] = 7, 9          # duplicates: the stable sort keeps their input order
+    for stable in (True, False):
+        for major, minor, nm in ((rows, cols, U), (cols, rows, I)):
+            a = csr_from_triples(major, minor, vals, nm, stable_sort=stable)
+            b = csr_from_triples(major, minor, vals, nm, stable_sort=stable, device="cpu")
+            assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
