@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -21,7 +22,7 @@ def _problem():
     return U, I, (indptr, keys, vals), (cind, ckeys, cvals), init_factors(U, 16, 16, 1, 0.1, True), init_factors(I, 16, 16, 2, 0.1, True)
 
 
-def _driver(P, Q, csr, rank, world, d):
+def _driver(P, Q, csr, rank, world, d, sharded_gram=False):
     import oracle
     from buffalo_b200.parallel.dist import ShardedALS
     o = oracle.OracleALS()
@@ -34,28 +35,44 @@ def _driver(P, Q, csr, rank, world, d):
         end = int(ind[hi - 1]) if hi > lo else beg
         o.partial_update(lo, hi, ind, np.ascontiguousarray(k[beg:max(end, beg + 1)]),
                          np.ascontiguousarray(v[beg:max(end, beg + 1)]), axis)
-    return ShardedALS(o.precompute, update, P, Q, rank, world, d)
+    class RangeGram(object):
+        """the two backend calls ShardedALS uses for the sharded Gram (CuALS.precompute_rows_device / gram_tensor)"""
+
+        def precompute_rows_device(self, axis, lo, hi):
+            F = (o.Q if axis == 0 else o.P)[lo:hi]
+            o.FF[:] = 0.0
+            if hi > lo:
+                oracle.lib().orc_als_precompute(oracle._f32(np.ascontiguousarray(F)), int(hi - lo), o.o.d, oracle._f32(o.FF),
+                                                o.o.num_workers)
+
+        def gram_tensor(self):
+            return torch.from_numpy(o.FF)      # shares memory: the all-reduce lands in the oracle's Gram
+    return ShardedALS(o.precompute, update, P, Q, rank, world, d, backend=RangeGram() if sharded_gram else None)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, sharded_gram=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     U, I, rw, cw, P0, Q0 = _problem()
     P, Q = torch.from_numpy(P0.copy()), torch.from_numpy(Q0.copy())
-    drv = _driver(P, Q, (rw, cw), rank, world, dist)
+    drv = _driver(P, Q, (rw, cw), rank, world, dist, sharded_gram)
+    assert drv.sharded_gram == sharded_gram
     for _ in range(2):
         drv.iteration()
     out[rank] = (P.numpy().copy(), Q.numpy().copy())
     dist.destroy_process_group()
 
 
-def test_sharded_equals_single_process():
+@pytest.mark.parametrize("sharded_gram", [False, True])
+def test_sharded_equals_single_process(sharded_gram):
+    """sharded_gram: every rank sums the Gram over its own rows of the opposite factor and the d x d partials are
+    all-reduced (what ShardedALS does with the CUDA backend) instead of each rank recomputing the full matrix."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, sharded_gram), nprocs=2, join=True)
     U, I, rw, cw, P0, Q0 = _problem()
     P, Q = torch.from_numpy(P0.copy()), torch.from_numpy(Q0.copy())
     single = _driver(P, Q, (rw, cw), 0, 1, None)
@@ -63,7 +80,8 @@ def test_sharded_equals_single_process():
         single.iteration()
     for r in (0, 1):
         Pr, Qr = out[r]
-        assert rel_err(Pr, P.numpy()) < 1e-6 and rel_err(Qr, Q.numpy()) < 1e-6      # replicas identical to 1-process run
+        tol = 1e-5 if sharded_gram else 1e-6     # the all-reduced Gram has a different fp32 summation order
+        assert rel_err(Pr, P.numpy()) < tol and rel_err(Qr, Q.numpy()) < tol          # replicas match the 1-process run
     assert not np.array_equal(P.numpy(), P0)
 
 
