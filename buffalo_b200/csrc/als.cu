@@ -15,7 +15,8 @@ struct bfl_als {
     int block_size = 32;
     bool adaptive_reg = false, compute_loss = true;
     float alpha = 8.f, reg_u = 0.1f, reg_i = 0.1f, eps = 1e-10f, cg_tolerance = 1e-10f;
-    int kernel_mode = 0;  // 0 auto (tuned SIMT kernels when applicable), 1 force generic, 3 tensor-core Gram variant (als_mma.cuh)
+    int kernel_mode = 0;  // 0 auto (tuned SIMT kernels when applicable), 1 force generic, 3 tensor-core Gram variant
+                          // (als_mma.cuh), 4 tuned kernels with rows of 513..1536 nnz on the re-gathering class
 
     // factors: either owned device mirrors of retained host pointers, or borrowed device memory
     float* hostP = nullptr;
@@ -157,7 +158,8 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     if (h->kernel_mode != 1 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
         const int32_t* left = nullptr;
         int64_t nleft = 0;
-        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, h->kernel_mode == 3);
+        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, h->kernel_mode == 3,
+                                 h->kernel_mode == 4 ? 1 : 0);
         if (rc != BFL_OK || nleft == 0) return rc;
         // rows longer than the tuned kernels accept go through the generic kernel
         a.row_list = left;

@@ -63,27 +63,33 @@ __host__ __device__ inline int fast_class_of(int64_t n) {
 }
 
 // ---- binning ------------------------------------------------------------------------------
+// long_regather: rows of 513..1536 nnz are sent to the re-gathering class (6) instead of the staged class (5)
+__host__ __device__ inline int fast_route(int64_t n, int long_regather) {
+    const int c = fast_class_of(n);
+    return (long_regather && c == 5) ? 6 : c;
+}
+
 __global__ void fast_count_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t row_end,
-                                  unsigned int* __restrict__ counts) {
+                                  unsigned int* __restrict__ counts, int long_regather) {
     __shared__ unsigned int c[FAST_NCLASS];
     if (threadIdx.x < FAST_NCLASS) c[threadIdx.x] = 0;
     __syncthreads();
     for (int64_t r = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_end;
          r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = indptr[r] - (r == 0 ? 0 : indptr[r - 1]);
-        if (n > 0) atomicAdd(&c[fast_class_of(n)], 1u);
+        if (n > 0) atomicAdd(&c[fast_route(n, long_regather)], 1u);
     }
     __syncthreads();
     if (threadIdx.x < FAST_NCLASS && c[threadIdx.x]) atomicAdd(counts + threadIdx.x, c[threadIdx.x]);
 }
 
 __global__ void fast_fill_kernel(const int64_t* __restrict__ indptr, int64_t row_begin, int64_t row_end,
-                                 unsigned int* __restrict__ cursors, int32_t* __restrict__ lists) {
+                                 unsigned int* __restrict__ cursors, int32_t* __restrict__ lists, int long_regather) {
     for (int64_t r = row_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < row_end;
          r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = indptr[r] - (r == 0 ? 0 : indptr[r - 1]);
         if (n > 0) {
-            const unsigned int pos = atomicAdd(cursors + fast_class_of(n), 1u);
+            const unsigned int pos = atomicAdd(cursors + fast_route(n, long_regather), 1u);
             lists[pos] = (int32_t)r;
         }
     }
@@ -583,7 +589,8 @@ int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
 // bins rows [row_begin,row_end) of a.indptr by length (cached per (indptr,row range)) and launches one
 // kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`
 inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cudaStream_t st,
-                           const int32_t** leftover_rows, int64_t* leftover_count, bool use_mma) {
+                           const int32_t** leftover_rows, int64_t* leftover_count, bool use_mma,
+                           int long_regather = 0) {
     *leftover_rows = nullptr;
     *leftover_count = 0;
     const int64_t nrows = a0.row_end - a0.row_begin;
@@ -599,7 +606,7 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         }
         BFL_CUDA(cudaMemsetAsync(fb->counters.p, 0, 2 * FAST_NCLASS * sizeof(unsigned int), st));
         const int grid = (int)std::min<int64_t>((nrows + 255) / 256, (int64_t)num_sms * 8);
-        fast_count_kernel<<<grid, 256, 0, st>>>(a0.indptr, a0.row_begin, a0.row_end, fb->counters.p);
+        fast_count_kernel<<<grid, 256, 0, st>>>(a0.indptr, a0.row_begin, a0.row_end, fb->counters.p, long_regather);
         BFL_LAUNCHED();
         BFL_CUDA(cudaMemcpyAsync(fb->count, fb->counters.p, FAST_NCLASS * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         BFL_CUDA(cudaStreamSynchronize(st));
@@ -608,7 +615,7 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         BFL_CUDA(cudaMemcpyAsync(fb->counters.p + FAST_NCLASS, fb->offset, FAST_NCLASS * sizeof(unsigned int),
                                  cudaMemcpyHostToDevice, st));
         fast_fill_kernel<<<grid, 256, 0, st>>>(a0.indptr, a0.row_begin, a0.row_end, fb->counters.p + FAST_NCLASS,
-                                               fb->lists.p);
+                                               fb->lists.p, long_regather);
         BFL_LAUNCHED();
         cache.bins[key] = fb;
     } else {

@@ -167,6 +167,9 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
         assert row_err.max() < 5e-3, (int(row_err.argmax()), int(lengths[row_err.argmax()]), float(row_err.max()))
         check_loss(nf, dnf, n0, dn0)
         check_loss(ns, dns, n0, dn0)
+        Xr, nr, dnr = gpu_half(dict(o, _b200_kernel_mode=4), P, Q, indptr, keys, vals, 0)   # 513..1536 re-gathered
+        assert rel_err(Xr, X0) < FACTOR_TOL
+        check_loss(nr, dnr, n0, dn0)
     # negative confidence values are legal input for every kernel variant
     vneg = vals.copy()
     vneg[::7] *= -0.25
