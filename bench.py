@@ -153,48 +153,105 @@ def measured_peak():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the restated oracle on the host cores (the reference cannot be built here)
 # ------------------------------------------------------------------------------------------------
-def cpu_sample_inputs(wl, Ph, Qh, frac_rows_u, frac_rows_i):
-    """Bounded sample of the SAME workload: the first rows of each orientation against the FULL opposite
-    factor matrix (what SURVEY.md 8d / BASELINE.md section 3 prescribe)."""
+def host_threads():
+    """Threads the CPU arm may really use: the scheduler affinity mask capped by the cgroup CPU quota (os.cpu_count()
+    ignores both; an oversubscribed OpenMP team made the round-1 reference number swing 6.5x between boxes)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:  # cgroup v2, then v1
+        if os.path.isfile("/sys/fs/cgroup/cpu.max"):
+            q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(p)
+        elif os.path.isfile("/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+    except Exception:
+        quota = None
+    used = n if quota is None else max(1, min(n, int(quota + 0.5)))
+    return used, {"affinity": n, "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
+
+
+def cpu_sample_inputs(wl, Ph, Qh, frac, seed=99):
+    """Bounded sample of the SAME workload: a seeded random subset of the rows of each orientation (compacted into a
+    small CSR + a gathered copy of their factor rows) against the FULL opposite factor matrix."""
+    rng = np.random.default_rng(seed)
     out = {}
-    for axis, (ind, keys, rows_total, frac) in enumerate([(wl["r_indptr"], wl["r_keys"], wl["U"], frac_rows_u),
-                                                          (wl["c_indptr"], wl["c_keys"], wl["I"], frac_rows_i)]):
+    for axis, (ind, keys, rows_total, F) in enumerate([(wl["r_indptr"], wl["r_keys"], wl["U"], Ph),
+                                                       (wl["c_indptr"], wl["c_keys"], wl["I"], Qh)]):
         n_rows = max(1, int(rows_total * frac))
-        hind = ind[:n_rows].cpu().numpy().astype(np.int64)
-        n = int(hind[-1])
-        out[axis] = dict(rows=n_rows, indptr=hind, keys=keys[:n].cpu().numpy(), vals=np.ones(n, np.float32), nnz=n)
-    out["P"] = Ph
-    out["Q"] = Qh
+        pick = np.sort(rng.choice(rows_total, size=n_rows, replace=False))
+        hind = ind.cpu().numpy().astype(np.int64) if hasattr(ind, "cpu") else np.asarray(ind, np.int64)
+        beg = np.where(pick > 0, hind[np.maximum(pick - 1, 0)], 0)
+        end = hind[pick]
+        lens = end - beg
+        sind = np.cumsum(lens).astype(np.int64)
+        n = int(sind[-1])
+        # gather the picked rows' keys on whatever device holds them
+        import torch
+        idx = np.repeat(beg - np.concatenate(([0], sind[:-1])), lens) + np.arange(n, dtype=np.int64)
+        kk = keys[torch.from_numpy(idx).to(keys.device)].cpu().numpy().astype(np.int32) if hasattr(keys, "device") \
+            else np.asarray(keys)[idx].astype(np.int32)
+        out[axis] = dict(rows=n_rows, indptr=sind, keys=kk, vals=np.ones(n, np.float32), nnz=n,
+                         F=np.ascontiguousarray(F[pick]), nnz_total=int(hind[-1]))
+    out["P"], out["Q"] = Ph, Qh
     return out
 
 
-def cpu_run(sample, opt, cores):
-    """One bounded CPU 'step': Gram + row solves for the sampled rows of both orientations. Returns (seconds, nnz)."""
+def cpu_run(sample, opt, threads):
+    """One bounded CPU 'step'.  The Gram of each FULL opposite matrix and the row solves of the sample are timed
+    separately and extrapolated to the full job:  T_full = T_gram(both) + sum_axis T_solve_sample / (sample nnz /
+    total nnz);  value = nnz / T_full with nnz counted ONCE per iteration, like the GPU arm."""
     import oracle
-    o = oracle.OracleALS()
-    o.init(dict(opt, num_workers=cores))
-    # the oracle updates the sampled rows in place (like training does); the opposite matrix is the full one
-    o.initialize_model(sample["P"], sample["Q"])
-    t0 = time.perf_counter()
-    nn = 0
+    t_gram, t_solve, t_full_solve = 0.0, 0.0, 0.0
     for axis in (0, 1):
         s = sample[axis]
+        o = oracle.OracleALS()
+        o.init(dict(opt, num_workers=threads))
+        if axis == 0:
+            o.initialize_model(s["F"].copy(), sample["Q"])
+        else:
+            o.initialize_model(sample["P"], s["F"].copy())
+        t0 = time.perf_counter()
         o.precompute(axis)
+        t1 = time.perf_counter()
         o.partial_update(0, s["rows"], s["indptr"], s["keys"], s["vals"], axis)
-        nn += s["nnz"]
-    return time.perf_counter() - t0, nn
+        t2 = time.perf_counter()
+        t_gram += t1 - t0
+        t_solve += t2 - t1
+        t_full_solve += (t2 - t1) * (s["nnz_total"] / max(1, s["nnz"]))
+    return dict(t_gram_s=t_gram, t_solve_s=t_solve, t_full_s=t_gram + t_full_solve,
+                frac=[sample[a]["nnz"] / max(1, sample[a]["nnz_total"]) for a in (0, 1)],
+                sample_nnz=sample[0]["nnz"] + sample[1]["nnz"])
 
 
-def size_cpu_sample(wl, Ph, Qh, opt, cores, target_s):
+def size_cpu_sample(wl, Ph, Qh, opt, threads, target_s):
     """Grow the row fraction until one CPU step lasts about target_s seconds (bounded sample)."""
     frac = 2e-4
-    for _ in range(4):
-        sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
-        t, nn = cpu_run(sample, opt, cores)
-        if t >= 0.4 * target_s or frac >= 0.05:
+    for _ in range(5):
+        sample = cpu_sample_inputs(wl, Ph, Qh, frac)
+        r = cpu_run(sample, opt, threads)
+        t = r["t_gram_s"] + r["t_solve_s"]
+        if t >= 0.5 * target_s or frac >= 0.05:
             break
-        frac = min(0.05, frac * max(2.0, min(20.0, 0.8 * target_s / max(t, 1e-3))))
+        grow = (0.8 * target_s - r["t_gram_s"]) / max(r["t_solve_s"], 1e-3)
+        frac = min(0.05, frac * max(1.5, min(20.0, grow)))
     return frac, sample
+
+
+def cpu_report(r, total_nnz, threads, tinfo, frac, kind="port"):
+    v = total_nnz / r["t_full_s"]
+    desc = ("seeded random %.4f%% of the user rows and of the item rows (%d nnz) solved against the full opposite "
+            "factors; Gram of both full matrices timed separately; extrapolated T_full = T_gram + T_solve/frac"
+            % (frac * 100, r["sample_nnz"]))
+    return v, {"value": v, "unit": "nnz/s", "cores": threads, "threads_used": threads, "thread_info": tinfo,
+               "kind": kind, "sample": desc, "t_gram_s": r["t_gram_s"], "t_solve_s": r["t_solve_s"],
+               "frac": r["frac"], "t_full_extrapolated_s": r["t_full_s"]}
 
 
 def main():
@@ -220,12 +277,12 @@ def main():
     w = WORKLOADS[args.workload]
     d = w["d"]
     opt = dict(ALS_OPT, d=d, _b200_kernel_mode=args.kernel_mode)
-    cores = os.cpu_count() or 1
+    cores, tinfo = host_threads()
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        return reference_arm(args, w, opt, cores)
+        return reference_arm(args, w, opt, cores, tinfo)
 
     assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU: there is no CPU fallback"
     import torch.distributed as dist
@@ -342,7 +399,7 @@ def main():
         out["e2e"] = e2e_sharded(args, wl, drv, d, device, P, Q, rank, world, dist)
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            out["cpu_baseline"] = cpu_baseline(args, wl, P, Q, opt, cores)
+            out["cpu_baseline"] = cpu_baseline(args, wl, P, Q, opt, cores, tinfo)
         except Exception as e:  # the oracle is test infrastructure; never fail the bench on it
             out["cpu_baseline"] = {"value": None, "error": str(e)}
     if rank == 0:
@@ -488,22 +545,18 @@ def e2e_host_path(args, wl, opt, d, device, Pd, Qd):
             "api": "bfl_als_partial_update (host CSR chunks, pinned)", "chunks_per_step": len(plan[0][1]) + len(plan[1][1])}
 
 
-def cpu_baseline(args, wl, P, Q, opt, cores):
+def cpu_baseline(args, wl, P, Q, opt, threads, tinfo):
     import oracle
     oracle.build()
     Ph, Qh = P.cpu().numpy(), Q.cpu().numpy()
-    frac, _ = size_cpu_sample(wl, Ph, Qh, opt, cores, args.cpu_seconds)
-    sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
-    t, nn = cpu_run(sample, opt, cores)
-    return {"value": nn / t, "unit": "nnz/s", "cores": cores, "kind": "port",
-            "sample": "first %.4f%% of user rows and of item rows (%d nnz) against the full opposite factors, "
-                      "Gram precompute of both full matrices included; %.1f s" % (frac * 100, nn, t),
-            "seconds": t}
+    frac, sample = size_cpu_sample(wl, Ph, Qh, opt, threads, args.cpu_seconds)
+    r = cpu_run(sample, opt, threads)
+    return cpu_report(r, wl["nnz"], threads, tinfo, frac)[1]
 
 
-def reference_arm(args, w, opt, cores):
-    """CPU arm: the restated reference path (oracle port; oracle/_ref cannot be built) on all host
-    cores, each step a bounded sample of the same workload."""
+def reference_arm(args, w, opt, threads, tinfo):
+    """CPU arm: the restated reference path (oracle port; oracle/_ref cannot be built) on the host threads
+    this process may use, each step a bounded random sample of the same workload, extrapolated to the full job."""
     import torch
     import oracle
     oracle.build()
@@ -518,25 +571,29 @@ def reference_arm(args, w, opt, cores):
     P = init_factors_t(wl["U"], d, device, 7)
     Q = init_factors_t(wl["I"], d, device, 8)
     Ph, Qh = P.cpu().numpy(), Q.cpu().numpy()
-    frac, _ = size_cpu_sample(wl, Ph, Qh, opt, cores, args.cpu_seconds)
-    sample = cpu_sample_inputs(wl, Ph, Qh, frac, frac)
+    frac, sample = size_cpu_sample(wl, Ph, Qh, opt, threads, args.cpu_seconds)
+    total_nnz = wl["nnz"]
     del wl
-    for _ in range(min(args.warmup, 1)):
-        cpu_run(sample, opt, cores)
-    tt, nn = 0.0, 0
+    for _ in range(args.warmup):
+        cpu_run(sample, opt, threads)
+    acc = None
     for _ in range(args.steps):
-        t, n = cpu_run(sample, opt, cores)
-        tt += t
-        nn += n
-    v = nn / tt
-    desc = ("each step: first %.4f%% of user rows and item rows (%d nnz) vs full opposite factors, Gram of both "
-            "full matrices included" % (frac * 100, nn // args.steps))
-    out = {"impl": "reference", "metric": "interactions/sec (nnz/s) ALS d=128", "value": v, "unit": "nnz/s",
-           "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": tt * 1e3 / args.steps,
+        r = cpu_run(sample, opt, threads)
+        if acc is None:
+            acc = dict(r)
+        else:
+            for k in ("t_gram_s", "t_solve_s", "t_full_s"):
+                acc[k] += r[k]
+    for k in ("t_gram_s", "t_solve_s", "t_full_s"):
+        acc[k] /= args.steps
+    v, cb = cpu_report(acc, total_nnz, threads, tinfo, frac)
+    out = {"impl": "reference", "metric": "interactions/sec (nnz/s) ALS d=%d" % d, "value": v, "unit": "nnz/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": acc["t_full_s"] * 1e3, "ms_per_step_measured_sample": (acc["t_gram_s"] + acc["t_solve_s"]) * 1e3,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["desc"], "users": w["users"], "items": w["items"], "nnz": w["nnz"], "d": d,
-                      "optimizer": "ialspp (d>=128)", "sampled": desc},
-           "cpu_baseline": {"value": v, "unit": "nnz/s", "cores": cores, "kind": "port", "sample": desc},
+                      "optimizer": "ialspp (d>=128)", "sampled": cb["sample"]},
+           "cpu_baseline": cb,
            "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

@@ -54,6 +54,10 @@ class SGDTrainerMixin(object):
 
     def _prepare_train(self):
         indptr, _, batch_size = self.buf.get_indptrs()
+        # a second train() (or user-replaced factors) arrives at width d: re-pad to vdim like bpr.py's _prepare_train,
+        # the native side copies rows * vdim floats in and out
+        self.P, self.Q = self._pad(self.P), self._pad(self.Q)
+        self.Qb = np.ascontiguousarray(self.Qb, dtype=np.float32).reshape(self.Q.shape[0], 1)
         self.obj.initialize_model(self.P, self.Q, self.Qb, self.num_nnz, True)
         self.obj.set_placeholder(indptr, batch_size)
         if hasattr(self, "sampling_table_"):

@@ -181,6 +181,12 @@ class CuSGD(object):
         return self._lib.bfl_sgd_get_vdim(self._h)
 
     def initialize_model(self, P, Q, Qb, num_nnz, set_gpu=True):
+        vdim = self.get_vdim()
+        if P.ndim != 2 or Q.ndim != 2 or P.shape[1] != vdim or Q.shape[1] != vdim:
+            raise ValueError("P and Q must be [rows, vdim=%d] (got %s, %s): the backend copies rows*vdim floats"
+                             % (vdim, P.shape, Q.shape))
+        if Qb.shape != (Q.shape[0], 1):
+            raise ValueError("Qb must be [%d, 1], got %s" % (Q.shape[0], Qb.shape))
         self._keep = [P, Q, Qb]
         _cabi.check(self._lib.bfl_sgd_initialize_model(self._h, _host(P, np.float32, 2, "P"), P.shape[0],
                                                        _host(Q, np.float32, 2, "Q"), Q.shape[0],

@@ -1,6 +1,6 @@
 // ALS backend: host-side state machine + C ABI (see include/buffalo_b200.h).
 // Replaces als::CALS (lib/algo_impl/als/als.cc) / cuda_als::CuALS (lib/cuda/als/als.cu).
-#include "als_mma.cuh"
+#include "als_fast.cuh"
 #include "als_generic.cuh"
 #include "bfl_common.cuh"
 
@@ -15,8 +15,10 @@ struct bfl_als {
     int block_size = 32;
     bool adaptive_reg = false, compute_loss = true;
     float alpha = 8.f, reg_u = 0.1f, reg_i = 0.1f, eps = 1e-10f, cg_tolerance = 1e-10f;
-    int kernel_mode = 0;  // 0 auto (tuned SIMT kernels when applicable), 1 force generic, 3 tensor-core Gram variant
-                          // (als_mma.cuh), 4 tuned kernels with rows of 513..1536 nnz on the re-gathering class
+    int kernel_mode = 0;  // 0 auto (d = 128: tensor-core kernel als_tc.cuh for rows above tc_min_nnz, tuned SIMT kernels
+                          // otherwise), 1 force generic, 2 tuned SIMT kernels only (the round-1 path), 4 SIMT only with
+                          // rows of 513..1536 nnz on the re-gathering class
+    int tc_min_class = 1; // first row-length class (als_fast.cuh) solved by the tensor-core kernel
 
     // factors: either owned device mirrors of retained host pointers, or borrowed device memory
     float* hostP = nullptr;
@@ -38,6 +40,7 @@ struct bfl_als {
     const float* d_vals[2] = {nullptr, nullptr};
     int64_t csr_rows[2] = {0, 0}, csr_nnz[2] = {0, 0};
     bool ph_set = false;
+    bool indptr_uploaded[2] = {false, false};   // own_indptr[axis] holds the caller's offsets (host-pointer path)
 
     DevBuf<float> G;          // d x d
     DevBuf<float> gram_part;  // partials of the two-stage Gram
@@ -67,6 +70,7 @@ int als_apply_options(bfl_als* h, const JsonOpt& j) {
     h->eps = (float)j.number("eps", 1e-10);
     h->cg_tolerance = (float)j.number("cg_tolerance", 1e-10);
     h->kernel_mode = j.integer("_b200_kernel_mode", 0);
+    h->tc_min_class = std::max(0, std::min(7, j.integer("_b200_tc_min_class", 1)));
     std::string optimizer = j.string("optimizer", "manual_cg");
     if (h->d >= 128) optimizer = "ialspp";  // als.cc:46
     if (optimizer == "llt") h->optimizer_code = 0;
@@ -158,8 +162,11 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     if (h->kernel_mode != 1 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
         const int32_t* left = nullptr;
         int64_t nleft = 0;
-        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, h->kernel_mode == 3,
-                                 h->kernel_mode == 4 ? 1 : 0);
+        // classes >= tcmin: fused tensor-core kernel (d = 128); class 7 (beyond the SIMT cap): split-row mode (d = 128, 256)
+        int tcmin = FAST_NCLASS;
+        if (h->kernel_mode == 0 && tc::tc_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) tcmin = h->tc_min_class;
+        else if (h->kernel_mode == 0 && tc::tc_split_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) tcmin = FAST_NCLASS - 1;
+        int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, tcmin, h->kernel_mode == 4 ? 1 : 0);
         if (rc != BFL_OK || nleft == 0) return rc;
         // rows longer than the tuned kernels accept go through the generic kernel
         a.row_list = left;
@@ -240,6 +247,16 @@ int bfl_als_initialize_model(bfl_als_t* h, float* P, int32_t P_rows, float* Q, i
     BFL_CUDA(cudaMemcpyAsync(h->dQ, Q, sizeof(float) * (size_t)Q_rows * h->vdim, cudaMemcpyHostToDevice, h->stream));
     BFL_CUDA(cudaStreamSynchronize(h->stream));
     h->factors_ready = true;
+    // a CSR bound earlier through bind_csr_device belongs to the previous model: drop the borrowed pointers
+    for (int ax = 0; ax < 2; ++ax) {
+        h->d_keys[ax] = nullptr;
+        h->d_vals[ax] = nullptr;
+        h->d_indptr[ax] = nullptr;
+        h->csr_rows[ax] = h->csr_nnz[ax] = 0;
+        h->indptr_uploaded[ax] = false;
+    }
+    h->ph_set = false;
+    h->fast_cache.clear();
     return BFL_OK;
 }
 
@@ -259,6 +276,7 @@ int bfl_als_set_placeholder(bfl_als_t* h, const int64_t* lindptr, const int64_t*
     }
     BFL_CUDA(cudaStreamSynchronize(h->stream));
     h->ph_set = true;
+    h->indptr_uploaded[0] = h->indptr_uploaded[1] = true;
     return BFL_OK;
 }
 
@@ -285,12 +303,13 @@ int bfl_als_partial_update(bfl_als_t* h, int32_t start_x, int32_t next_x, const 
     const int64_t rows = axis == 0 ? h->P_rows : h->Q_rows;
     if (start_x < 0 || next_x > rows || next_x < start_x || !indptr || !keys || !vals)
         BFL_FAIL(BFL_ERR_ARG, "bad chunk arguments");
-    if (!h->ph_set || h->d_indptr[axis] != h->own_indptr[axis].p) {
+    if (!h->indptr_uploaded[axis] || h->d_indptr[axis] != h->own_indptr[axis].p) {
         // the CPU holder needs no set_placeholder (als.py:156-158 only calls it for the accelerator);
         // upload this axis' end offsets on first use
         if (BFL_OK != h->own_indptr[axis].reserve((size_t)rows)) return BFL_ERR_CUDA;
         BFL_CUDA(cudaMemcpyAsync(h->own_indptr[axis].p, indptr, sizeof(int64_t) * rows, cudaMemcpyHostToDevice, h->stream));
         h->d_indptr[axis] = h->own_indptr[axis].p;
+        h->indptr_uploaded[axis] = true;
         h->fast_cache.clear();
     }
     const int64_t beg = start_x == 0 ? 0 : indptr[start_x - 1];
@@ -379,6 +398,7 @@ int bfl_als_bind_csr_device(bfl_als_t* h, int axis, const int64_t* d_indptr, con
     if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
     if (!d_indptr || (nnz > 0 && (!d_keys || !d_vals)) || rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad CSR arguments");
     h->fast_cache.clear();
+    h->indptr_uploaded[axis] = false;
     h->d_indptr[axis] = d_indptr;
     h->d_keys[axis] = d_keys;
     h->d_vals[axis] = d_vals;

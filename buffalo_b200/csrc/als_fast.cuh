@@ -27,7 +27,9 @@
 #include <algorithm>
 #include <map>
 
+#include "als_explicit.cuh"
 #include "als_generic.cuh"
+#include "als_tc.cuh"
 #include "bfl_common.cuh"
 
 namespace bfl {
@@ -535,16 +537,17 @@ __global__ void __launch_bounds__(FAST_THREADS, 1) als_ialspp_team_kernel(AlsArg
 }
 
 // ---- host side --------------------------------------------------------------------------------
-// tensor-core variant (als_mma.cuh)
-inline bool mma_class_covered(int c);
-inline int mma_launch(int c, const AlsArgs& a, int cap, int num_sms, cudaStream_t st);
-
 struct FastBins {
     DevBuf<int32_t> lists;           // all classes back to back
     DevBuf<unsigned int> counters;   // [0..7] counts, [8..15] cursors
     unsigned int count[FAST_NCLASS] = {0};
     unsigned int offset[FAST_NCLASS + 1] = {0};
+    // split-row work items of class 7 (rows beyond FAST_NR_CAP): triples (row, chunk, slot), see als_tc.cuh
+    DevBuf<int32_t> items;
+    DevBuf<unsigned long long> item_counter;
+    int64_t n_items = -1;
 };
+constexpr int64_t TC_SPLIT = 8192;   // nnz per chunk of a split row
 struct FastBinKey {
     const void* indptr; int64_t b, e;
     bool operator<(const FastBinKey& o) const {
@@ -555,6 +558,7 @@ struct FastBinKey {
 };
 struct FastCache {
     std::map<FastBinKey, FastBins*> bins;
+    DevBuf<float> scratch;   // partial matrices of the split rows (als_tc.cuh PARTIAL mode)
     void clear() {
         for (auto& kv : bins) delete kv.second;
         bins.clear();
@@ -571,12 +575,9 @@ template <int W, int K, int KS, bool RES, bool GSM>
 int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
     const size_t smem = fast_smem_bytes(a.D, W, K, KS, RES, GSM, cap);
     constexpr int SMEM_MAX = 227 * 1024;
-    static bool configured = false;
-    if (!configured) {
-        BFL_CUDA(cudaFuncSetAttribute(als_ialspp_team_kernel<W, K, KS, RES, GSM>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
-        configured = true;
-    }
+    // per device/context attribute: set it on every launch (a process may drive several GPUs)
+    BFL_CUDA(cudaFuncSetAttribute(als_ialspp_team_kernel<W, K, KS, RES, GSM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     if (smem > (size_t)SMEM_MAX) BFL_FAIL(BFL_ERR_STATE, "tuned ALS kernel: shared memory budget exceeded");
     const int64_t nrows = a.row_end - a.row_begin;
     constexpr int TEAMS = FAST_WARPS / W;
@@ -587,9 +588,11 @@ int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
 }
 
 // bins rows [row_begin,row_end) of a.indptr by length (cached per (indptr,row range)) and launches one
-// kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`
+// kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`.
+// tc_min_class <= 7: classes >= tc_min_class (including 7, rows of any length) are solved by ONE launch of the
+// tensor-core kernel (als_tc.cuh) over their contiguous part of the binned list.
 inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cudaStream_t st,
-                           const int32_t** leftover_rows, int64_t* leftover_count, bool use_mma,
+                           const int32_t** leftover_rows, int64_t* leftover_count, int tc_min_class,
                            int long_regather = 0) {
     *leftover_rows = nullptr;
     *leftover_count = 0;
@@ -621,7 +624,51 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
     } else {
         fb = it->second;
     }
-    for (int c = 0; c < FAST_NCLASS - 1; ++c) {
+    if (tc_min_class < FAST_NCLASS && fb->count[FAST_NCLASS - 1]) {
+        // rows beyond FAST_NR_CAP (any length): cut into chunks spread over the SMs, partial matrices summed in global
+        // memory, then the explicit-matrix solve
+        const int64_t n7 = fb->count[FAST_NCLASS - 1];
+        const int32_t* list7 = fb->lists.p + fb->offset[FAST_NCLASS - 1];
+        if (fb->n_items < 0) {
+            if (BFL_OK != fb->item_counter.reserve(2)) return BFL_ERR_CUDA;
+            BFL_CUDA(cudaMemsetAsync(fb->item_counter.p, 0, 2 * sizeof(unsigned long long), st));
+            const int g7 = (int)std::min<int64_t>((n7 + 127) / 128, 1024);
+            tc::tc_count_items_kernel<<<g7, 128, 0, st>>>(a0.indptr, list7, n7, TC_SPLIT, fb->item_counter.p);
+            BFL_LAUNCHED();
+            unsigned long long total = 0;
+            BFL_CUDA(cudaMemcpyAsync(&total, fb->item_counter.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+            BFL_CUDA(cudaStreamSynchronize(st));
+            if (BFL_OK != fb->items.reserve(3 * (size_t)total)) return BFL_ERR_CUDA;
+            tc::tc_fill_items_kernel<<<g7, 128, 0, st>>>(a0.indptr, list7, n7, TC_SPLIT, fb->item_counter.p + 1, fb->items.p);
+            BFL_LAUNCHED();
+            fb->n_items = (int64_t)total;
+        }
+        const size_t sf = a0.D == 128 ? tc::scratch_floats<128>() : tc::scratch_floats<256>();
+        if (BFL_OK != cache.scratch.reserve(sf * (size_t)n7)) return BFL_ERR_CUDA;
+        int rc = a0.D == 128
+                     ? tc::tc_launch_partial<128>(a0, fb->items.p, fb->n_items, cache.scratch.p, n7, TC_SPLIT, num_sms, st)
+                     : tc::tc_launch_partial<256>(a0, fb->items.p, fb->n_items, cache.scratch.p, n7, TC_SPLIT, num_sms, st);
+        if (rc != BFL_OK) return rc;
+        ExplicitArgs ea;
+        ea.a = a0;
+        ea.a.row_list = list7;
+        ea.a.row_begin = 0;
+        ea.a.row_end = n7;
+        ea.scratch = cache.scratch.p;
+        const int ge = (int)std::min<int64_t>(n7, (int64_t)num_sms * 4);
+        if (a0.D == 128) als_explicit_solve_kernel<128><<<ge, 128, 0, st>>>(ea);
+        else als_explicit_solve_kernel<256><<<ge, 256, 0, st>>>(ea);
+        BFL_LAUNCHED();
+    }
+    if (tc_min_class < FAST_NCLASS - 1 && fb->offset[FAST_NCLASS - 1] > fb->offset[tc_min_class]) {
+        AlsArgs a = a0;
+        a.row_list = fb->lists.p;
+        a.row_begin = fb->offset[tc_min_class];
+        a.row_end = fb->offset[FAST_NCLASS - 1];
+        const int rc = tc::tc_launch(a, num_sms, st);
+        if (rc != BFL_OK) return rc;
+    }
+    for (int c = 0; c < std::min(FAST_NCLASS - 1, tc_min_class); ++c) {
         if (!fb->count[c]) continue;
         AlsArgs a = a0;
         a.row_list = fb->lists.p;
@@ -629,11 +676,6 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         a.row_end = fb->offset[c + 1];
         const FastClass fc = fast_class(c);
         int rc = BFL_OK;
-        if (use_mma && a.D <= 128 && mma_class_covered(c)) {
-            rc = mma_launch(c, a, fc.cap, num_sms, st);
-            if (rc != BFL_OK) return rc;
-            continue;
-        }
         const bool gsm = a.D <= 128;   // d x (d+4) floats of Gram fit next to the staging buffers only up to d = 128
         switch (c) {
             case 0: rc = gsm ? fast_launch_class<1, 1, 0, true, true>(a, fc.cap, num_sms, st)
@@ -652,7 +694,7 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         }
         if (rc != BFL_OK) return rc;
     }
-    if (fb->count[FAST_NCLASS - 1]) {
+    if (tc_min_class >= FAST_NCLASS && fb->count[FAST_NCLASS - 1]) {
         *leftover_rows = fb->lists.p + fb->offset[FAST_NCLASS - 1];
         *leftover_count = fb->count[FAST_NCLASS - 1];
     }

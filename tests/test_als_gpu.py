@@ -137,10 +137,11 @@ def test_c1_config_training_trajectory(cuda_lib):
 
 @pytest.mark.parametrize("d", [128, 64, 32, 96, 256])
 def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
-    """The tuned iALS++ kernels bin rows by length (<=32, 64, 128, 256, 512 register-resident; <=1536 two register
-    tiles + one shared-memory tile per warp, SIMT kernel by default, tensor-core Gram variant with
-    _b200_kernel_mode=3; <=12288 re-gathering SIMT kernel; longer rows fall back to the generic kernel).
-    One input that hits every class, checked against the oracle and the generic kernel (_b200_kernel_mode=1)."""
+    """Rows are binned by length (<=32, 64, 128, 256, 512, 1536, 12288, longer).  Default (_b200_kernel_mode=0):
+    at d=128 every row above 32 nnz goes through the tcgen05 kernel (als_tc.cuh: fused up to 12288 nnz, split-row +
+    explicit solve beyond), at d=256 the rows beyond 12288 do, everything else through the tuned SIMT kernels;
+    _b200_kernel_mode=2 = SIMT kernels only (rows beyond 12288 on the generic kernel), 1 = generic kernels.
+    One input that hits every class, checked against the oracle and the generic kernel."""
     rng = np.random.default_rng(d)
     lengths = np.concatenate([rng.integers(1, 33, 300), rng.integers(33, 65, 200), rng.integers(65, 129, 150),
                               rng.integers(129, 257, 80), rng.integers(257, 513, 40), rng.integers(513, 1025, 20),
@@ -159,7 +160,7 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
         X0, n0, dn0 = oracle_half(o, P, Q, indptr, keys, vals, 0)
         Xf, nf, dnf = gpu_half(o, P, Q, indptr, keys, vals, 0)
         Xg, ng, dng = gpu_half(dict(o, _b200_kernel_mode=1), P, Q, indptr, keys, vals, 0)
-        Xs, ns, dns = gpu_half(dict(o, _b200_kernel_mode=3), P, Q, indptr, keys, vals, 0)   # tensor-core Gram variant
+        Xs, ns, dns = gpu_half(dict(o, _b200_kernel_mode=2), P, Q, indptr, keys, vals, 0)   # SIMT kernels only
         assert rel_err(Xf, X0) < FACTOR_TOL and rel_err(Xg, X0) < FACTOR_TOL and rel_err(Xs, X0) < FACTOR_TOL
         assert rel_err(Xf, Xg) < FACTOR_TOL
         # no single row is off either (the Frobenius norm would hide one bad row-length class)
@@ -174,7 +175,7 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
     vneg = vals.copy()
     vneg[::7] *= -0.25
     X0, n0, dn0 = oracle_half(opt, P, Q, indptr, keys, vneg, 0)
-    for mode in (0, 3):
+    for mode in (0, 2):
         Xf, nf, dnf = gpu_half(dict(opt, _b200_kernel_mode=mode), P, Q, indptr, keys, vneg, 0)
         assert np.isfinite(Xf).all() and rel_err(Xf, X0) < FACTOR_TOL, mode
     # item side (loss has the extra x G x and observed terms): reuse the same CSR as a colwise matrix
@@ -184,6 +185,70 @@ def test_tuned_kernel_all_row_length_classes(cuda_lib, d):
     Xf, nf, dnf = gpu_half(opt, Pi, Qi, indptr, keys, vals, 1)
     assert rel_err(Xf, X0) < FACTOR_TOL
     check_loss(nf, dnf, n0, dn0)
+
+
+@pytest.mark.parametrize("d", [128, 256])
+def test_long_rows_split_tensor_core_path(cuda_lib, d):
+    """Rows far beyond the SIMT kernels' cap (2e4, 2e5 and 1e6 nnz; Zipf head items of BASELINE configs[4]) are cut into
+    8192-entry chunks over the SMs, their explicit matrices summed by the tcgen05 kernel and solved by
+    als_explicit_solve_kernel.  Bar: 1e-3 against the fp32 oracle; where the oracle's own sequential fp32 sums over
+    1e6 terms drift further than that from the fp64 mirror, the GPU must be at least as close to the mirror."""
+    from oracle import np_mirror
+    rng = np.random.default_rng(d + 1)
+    lengths = np.array([20000, 200000, 1000000, 700, 12289, 40, 16385, 8193], dtype=np.int64)
+    U, I = len(lengths), 1_200_000
+    keys = np.concatenate([np.sort(rng.choice(I, size=n, replace=False)) for n in lengths]).astype(np.int32)
+    indptr = np.cumsum(lengths).astype(np.int64)
+    vals = rng.integers(1, 4, len(keys)).astype(np.float32)
+    opt = full_opt(d=d, optimizer="ialspp", block_size=32)
+    P = init_factors(U, d, d, 1, scale=0.05, signed=True)
+    Q = init_factors(I, d, d, 2, scale=0.05, signed=True)
+    for axis in (0, 1):
+        # axis 1 exercises the loss pieces (x G x, observed terms) of the split path: same CSR read as a colwise matrix
+        Pa, Qa = (P, Q) if axis == 0 else (Q, P)
+        X0, n0, dn0 = oracle_half(opt, Pa, Qa, indptr, keys, vals, axis)
+        Xf, nf, dnf = gpu_half(opt, Pa, Qa, indptr, keys, vals, axis)
+        row_err = np.linalg.norm(Xf - X0, axis=1) / np.maximum(np.linalg.norm(X0, axis=1), 1e-6)
+        if row_err.max() >= FACTOR_TOL:
+            # judge against the fp64 mirror row by row
+            Xup, Yop = (Pa, Qa) if axis == 0 else (Qa, Pa)
+            Xm, _, _ = np_mirror.als_half_epoch(Xup[:U], Yop, indptr, keys, vals, opt, axis)
+            eg = np.linalg.norm(Xf - Xm, axis=1) / np.maximum(np.linalg.norm(Xm, axis=1), 1e-6)
+            eo = np.linalg.norm(X0 - Xm, axis=1) / np.maximum(np.linalg.norm(Xm, axis=1), 1e-6)
+            assert (eg <= np.maximum(eo * 1.5, FACTOR_TOL)).all(), (axis, eg.tolist(), eo.tolist())
+        assert np.isfinite(Xf).all()
+        assert abs(nf - n0) <= 2e-4 * max(1.0, abs(n0)), (nf, n0)
+        assert abs(dnf - dn0) <= 1e-4 * max(1.0, abs(dn0)), (dnf, dn0)
+
+
+def test_d128_reference_init_three_iterations(cuda_lib):
+    """The benched state: d=128 from the reference's own abs(N(0, 1/d^2)) initialisation (als.py:85-86), three full
+    iterations.  There the Gram matrix is numerically rank-one and the fp32 oracle itself sits 1e-2..1e-1 away from
+    the fp64 mirror on the first passes, so the bar is: per half-epoch, started from the oracle's state,
+    the GPU is no further from the oracle than the oracle is from the fp64 mirror (or within 1e-3), and the RMSE of the
+    GPU's own trajectory matches the oracle's."""
+    from oracle import np_mirror
+    U, I, nnz, d = 1500, 900, 60000, 128
+    indptr, keys, vals, _ = make_csr(U, I, nnz, seed=4321)
+    cind, ckeys, cvals = transpose_csr(indptr, keys, vals, U, I)
+    opt = full_opt(d=d)
+    Pg = init_factors(U, d, d, 7)
+    Qg = init_factors(I, d, d, 8)
+    Po, Qo = Pg.copy(), Qg.copy()
+    for it in range(3):
+        Ps, _, _ = gpu_half(opt, Po, Qo, indptr, keys, vals, 0)
+        Pm, _, _ = np_mirror.als_half_epoch(Po, Qo, indptr, keys, vals, opt, 0)
+        Pg, n1, d1 = gpu_half(opt, Pg, Qg, indptr, keys, vals, 0)
+        Po, m1, e1 = oracle_half(opt, Po, Qo, indptr, keys, vals, 0)
+        assert rel_err(Ps, Po) <= max(FACTOR_TOL, 1.5 * rel_err(Po, Pm)), (it, rel_err(Ps, Po), rel_err(Po, Pm))
+        Qs, _, _ = gpu_half(opt, Po, Qo, cind, ckeys, cvals, 1)
+        Qm, _, _ = np_mirror.als_half_epoch(Qo, Po, cind, ckeys, cvals, opt, 1)
+        Qg, n2, d2 = gpu_half(opt, Pg, Qg, cind, ckeys, cvals, 1)
+        Qo, m2, e2 = oracle_half(opt, Po, Qo, cind, ckeys, cvals, 1)
+        assert rel_err(Qs, Qo) <= max(FACTOR_TOL, 1.5 * rel_err(Qo, Qm)), (it, rel_err(Qs, Qo), rel_err(Qo, Qm))
+        rmse_g = ((n1 + n2) / (d1 + d2 + 1e-10)) ** 0.5     # als.py:171
+        rmse_o = ((m1 + m2) / (e1 + e2 + 1e-10)) ** 0.5
+        assert abs(rmse_g - rmse_o) <= 2e-3 * rmse_o, (it, rmse_g, rmse_o)
 
 
 def test_chunked_equals_whole_and_placeholder(cuda_lib):
