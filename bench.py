@@ -29,8 +29,12 @@ WORKLOADS = {
                desc="ALS d=128 10Mx1M 1B-nnz synthetic CSR (BASELINE configs[1])"),
     "c2_small": dict(users=1_000_000, items=100_000, nnz=100_000_000, d=128,
                      desc="1/10-scale C2 (debug only; NOT the headline workload)"),
-    "c5_small": dict(users=500_000, items=50_000, nnz=200_000_000, d=256,
-                     desc="1/10-scale, uniform-item stand-in for BASELINE configs[4] (d=256; debug only)"),
+    "c5": dict(users=5_000_000, items=500_000, nnz=2_000_000_000, d=256, zipf=1.1,
+               desc="ALS d=256 Zipf(1.1) items 5Mx500k ~2B-nnz synthetic CSR (BASELINE configs[4])"),
+    "c5_small": dict(users=500_000, items=50_000, nnz=200_000_000, d=256, zipf=1.1,
+                     desc="1/10-scale BASELINE configs[4] (d=256, Zipf(1.1) items; debug only)"),
+    "c5_d128": dict(users=500_000, items=50_000, nnz=200_000_000, d=128, zipf=1.1,
+                    desc="1/10-scale Zipf(1.1) workload at d=128 (long-row path of the tensor-core kernel; debug only)"),
     "tiny": dict(users=20_000, items=5_000, nnz=1_000_000, d=128, desc="smoke-scale (debug only)"),
 }
 ALS_OPT = dict(d=128, optimizer="manual_cg", num_workers=1, compute_loss_on_training=False, alpha=8.0, reg_u=0.1,
@@ -50,6 +54,8 @@ def make_workload(w, device, seed=2024):
     (the reference sorts by (row, col), fileio.hpp:330-341), values 1.0.  Returns dict of device tensors:
     rowwise (indptr_end, keys), colwise (indptr_end, keys), shared vals."""
     import torch
+    if w.get("zipf"):
+        return make_workload_zipf(w, device, seed=2027)
     U, I, nnz = w["users"], w["items"], w["nnz"]
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -84,6 +90,66 @@ def make_workload(w, device, seed=2024):
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     return dict(U=U, I=I, nnz=nnz, r_indptr=r_indptr, r_keys=r_keys, c_indptr=c_indptr, c_keys=c_keys, vals=vals)
+
+
+def make_workload_zipf(w, device, seed=2027):
+    """SURVEY.md 8(d) generator C5: per-user degree ~ clipped lognormal, items ~ Zipf(alpha) over the item range by
+    inverse-CDF sampling, duplicates within a user removed (so an item's degree is capped at the number of users), keys
+    sorted within rows, values 1.0.  The draw count is inflated by the expected duplicate rate so that the
+    de-duplicated matrix lands near the nominal nnz; the actual nnz is reported."""
+    import torch
+    U, I, nnz, alpha = w["users"], w["items"], w["nnz"], float(w["zipf"])
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    pmf = torch.arange(1, I + 1, device=device, dtype=torch.float64) ** (-alpha)
+    pmf /= pmf.sum()
+    mean_deg = nnz / U
+    # expected distinct items among m draws: sum_k 1 - (1 - p_k)^m ; pick the per-user draw count whose expectation is mean_deg
+    lo, hi = mean_deg, mean_deg * 4
+    for _ in range(30):
+        mid = 0.5 * (lo + hi)
+        if float((1.0 - torch.exp(mid * torch.log1p(-pmf))).sum().item()) < mean_deg:
+            lo = mid
+        else:
+            hi = mid
+    inflate = hi / mean_deg
+    sigma = 0.5
+    mu = np.log(mean_deg * inflate) - 0.5 * sigma * sigma
+    deg = torch.exp(torch.randn(U, device=device, generator=g, dtype=torch.float32) * sigma + mu)
+    deg = torch.clamp(deg, max=float(I) / 4).round().to(torch.int64)
+    draws = int(deg.sum().item())
+    cdf = torch.cumsum(pmf, 0).to(torch.float32)
+    cdf[-1] = 1.0
+    rows = torch.repeat_interleave(torch.arange(U, device=device, dtype=torch.int64), deg)
+    key = torch.empty(draws, device=device, dtype=torch.int64)
+    step = 1 << 28
+    for s0 in range(0, draws, step):
+        u = torch.rand(min(step, draws - s0), device=device, generator=g, dtype=torch.float32)
+        col = torch.searchsorted(cdf, u).clamp_(max=I - 1)
+        key[s0:s0 + len(u)] = rows[s0:s0 + len(u)] * I + col
+        del u, col
+    del rows, deg
+    key = torch.sort(key).values
+    key = torch.unique_consecutive(key)
+    nnz = int(key.numel())
+    r_keys = (key % I).to(torch.int32)
+    rows = key // I
+    del key
+    r_indptr = torch.cumsum(torch.bincount(rows, minlength=U), 0)
+    key2 = r_keys.to(torch.int64) * U + rows
+    del rows
+    key2 = torch.sort(key2).values
+    c_keys = (key2 % U).to(torch.int32)
+    c_cols = key2 // U
+    del key2
+    c_indptr = torch.cumsum(torch.bincount(c_cols, minlength=I), 0)
+    del c_cols
+    vals = torch.ones(nnz, device=device, dtype=torch.float32)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    return dict(U=U, I=I, nnz=nnz, r_indptr=r_indptr, r_keys=r_keys, c_indptr=c_indptr, c_keys=c_keys, vals=vals,
+                inflate=inflate)
 
 
 def init_factors_t(rows, d, device, seed):
@@ -382,7 +448,7 @@ def main():
                 "launch_ms": {"user_pass": float(np.mean(per_axis_ms[0])), "item_pass": float(np.mean(per_axis_ms[1]))},
                 "share_of_step": t_solve * 1e3 * args.steps / ms}
 
-    out = {"metric": "interactions/sec (nnz/s) ALS d=128", "value": value, "unit": "nnz/s", "n_gpus": world,
+    out = {"metric": "interactions/sec (nnz/s) ALS d=%d" % d, "value": value, "unit": "nnz/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["desc"], "users": U, "items": I, "nnz": nnz, "d": d, "optimizer": "ialspp (d>=128)",

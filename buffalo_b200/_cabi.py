@@ -77,6 +77,9 @@ PROTOTYPES = {
     "bfl_sgd_epoch": (C.c_int, [_vp]),
     "bfl_sgd_current_lr": (_d, [_vp]),
     "bfl_sgd_read_stats": (C.c_int, [_vp, _pd, _pi64]),
+    # evaluation top-k
+    "bfl_topk_device": (C.c_int, [_vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "bfl_topk_host": (C.c_int, [_vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
 }
 
 

@@ -99,6 +99,11 @@ class Algo(abc.ABC):
         if pool is not None:
             Q = Q[pool]
             Qb = Qb[pool] if Qb is not None else None
+        from buffalo_b200 import backend
+        if backend.device_available() and 0 < topk <= 4096 and Q.shape[0] >= 1:
+            # scores and top-k on the device (csrc/topk.cu); pb is constant per query row and does not change the order
+            topks = backend.topk_host(p, Q, Qb, topk)
+            return topks if pool is None else np.array([pool[t] for t in topks])
         scores = p.dot(Q.T)
         if pb is not None:
             scores += pb

@@ -8,6 +8,7 @@ streams only).
 """
 import ctypes as C
 import json
+import os
 
 import numpy as np
 
@@ -301,3 +302,45 @@ class CuSGD(object):
         loss, n = C.c_double(0.0), C.c_int64(0)
         _cabi.check(self._lib.bfl_sgd_read_stats(self._h, C.byref(loss), C.byref(n)), "read_stats")
         return loss.value, n.value
+
+
+def device_available():
+    """True when the CUDA library is loadable and a GPU is visible (used by host-side helpers that have a device
+    implementation; the training backends never consult this: they fail loudly without a GPU)."""
+    try:
+        import torch
+        return bool(torch.cuda.is_available()) and os.path.isfile(_cabi.LIB_PATH)
+    except Exception:
+        return False
+
+
+def topk_host(queries, items, item_bias, k):
+    """k best item indices per query row for scores = queries @ items.T (+ item_bias), best first, computed on the
+    device (bfl_topk_host).  queries [nq, d], items [I, d] float32 host arrays; returns int32 [nq, k]."""
+    q = np.ascontiguousarray(queries, dtype=np.float32)
+    it = np.ascontiguousarray(items, dtype=np.float32)
+    if q.ndim == 1:
+        q = q.reshape(1, -1)
+    d = min(q.shape[1], it.shape[1])
+    k = int(min(k, it.shape[0]))
+    out = np.empty((q.shape[0], k), dtype=np.int32)
+    b = None if item_bias is None else np.ascontiguousarray(np.asarray(item_bias, dtype=np.float32).reshape(-1))
+    _cabi.check(_cabi.lib().bfl_topk_host(q.ctypes.data, q.shape[0], q.shape[1], it.ctypes.data, it.shape[0],
+                                          it.shape[1], None if b is None else b.ctypes.data, int(d), k,
+                                          out.ctypes.data, None), "bfl_topk_host")
+    return out
+
+
+def topk_device(queries, items, item_bias, k, stream=None):
+    """Device tensors in, device tensors out: (idx int32 [nq, k], val float32 [nq, k])."""
+    import torch
+    nq, n_items = queries.shape[0], items.shape[0]
+    k = int(min(k, n_items))
+    idx = torch.empty((nq, k), dtype=torch.int32, device=queries.device)
+    val = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+    _cabi.check(_cabi.lib().bfl_topk_device(_dev(queries, "float32", "queries"), nq, queries.stride(0),
+                                            _dev(items, "float32", "items"), n_items, items.stride(0),
+                                            None if item_bias is None else _dev(item_bias, "float32", "bias"),
+                                            int(min(queries.shape[1], items.shape[1])), k, idx.data_ptr(), val.data_ptr(),
+                                            _stream_ptr(stream)), "bfl_topk_device")
+    return idx, val

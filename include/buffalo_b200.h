@@ -216,6 +216,20 @@ int bfl_sgd_epoch(bfl_sgd_t* h);
 double bfl_sgd_current_lr(bfl_sgd_t* h);
 int bfl_sgd_read_stats(bfl_sgd_t* h, double* loss_sum, int64_t* num_updates);
 
+/* =====================================================================================
+ * Evaluation top-k; replaces the host quickselect behind Evaluable.get_topk /
+ * Algo._get_topk_recommendation (buffalo/evaluate/base.py:31-42, buffalo/parallel/_core.hpp:69-142):
+ * scores = queries . items^T (+ item_bias), the k best item indices per query, best first; ties go to the
+ * smaller index; -1 pads when there are fewer than k items.  k <= 4096.
+ * ===================================================================================== */
+/* device pointers, stream-ordered */
+int bfl_topk_device(const float* d_queries, int64_t nq, int ldq, const float* d_items, int64_t n_items, int ldi,
+                    const float* d_item_bias /* nullable */, int d, int k, int32_t* d_out_idx, float* d_out_val,
+                    void* stream);
+/* host pointers (copies in, runs, copies out); out_val may be NULL */
+int bfl_topk_host(const float* queries, int64_t nq, int ldq, const float* items, int64_t n_items, int ldi,
+                  const float* item_bias /* nullable */, int d, int k, int32_t* out_idx, float* out_val);
+
 #ifdef __cplusplus
 }
 #endif
