@@ -62,7 +62,16 @@ def test_algo_topk_recommendation_uses_device(cuda_lib):
     rng = np.random.default_rng(5)
     P = rng.normal(size=(40, 24)).astype(np.float32)
     Q = rng.normal(size=(3000, 24)).astype(np.float32)
-    a = Algo.__new__(Algo)
+    class _A(Algo):
+        def _get_feature(self, *a, **k):
+            return None
+
+        def normalize(self, *a, **k):
+            return None
+
+        def get_topk(self, scores, k, sorted=True, num_threads=4):
+            return topk_indices(scores, k)
+    a = _A.__new__(_A)
     got = Algo._get_topk_recommendation(a, P, Q, None, None, None, 12, 1)
     want = topk_indices(P @ Q.T, 12)
     assert (np.asarray(got) == want).mean() > 0.99
