@@ -326,7 +326,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("BFL_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="als", choices=["als", "bpr", "warp"],
+                    help="als (default; the headline metric) or the BPRMF / WARP epochs of BASELINE configs[2], [3]")
+    ap.add_argument("--optimizer", default=None, help="bpr/warp only: sgd | adagrad | adam (default: the reference's)")
+    ap.add_argument("--workload", default=os.environ.get("BFL_BENCH_WORKLOAD"),
+                    help="als: %s; bpr: c3, c3_small; warp: c4, c4_small" % ", ".join(sorted(WORKLOADS)))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -334,6 +338,14 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("BFL_EXCHANGE", "p2p"), choices=["p2p", "allgather"],
                     help="multi-GPU: fused peer stores from the solve kernel (default) or an NCCL all-gather per half-epoch")
     args = ap.parse_args()
+    if args.algo != "als":
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import sgd_bench
+        args.workload = args.workload or ("c3" if args.algo == "bpr" else "c4")
+        assert args.workload in sgd_bench.SGD_WORKLOADS and sgd_bench.SGD_WORKLOADS[args.workload]["algo"] == args.algo
+        return sgd_bench.main(args)
+    args.workload = args.workload or "c2"
+    assert args.workload in WORKLOADS, "unknown ALS workload %s" % args.workload
     assert args.warmup >= 3 or args.workload != "c2" or args.impl == "reference", "timing rules: warmup >= 3"
 
     import torch

@@ -215,18 +215,35 @@ class ShardedSGD(object):
                 self.dist.all_reduce(g)
             self.apply()
             return
-        q0 = self.Q.clone()
-        b0 = self.Qb.clone() if self.Qb is not None else None
+        # plain-SGD BPR: only the item side is shared.  Every rank reads and writes ONLY its own users' rows of P
+        # during training, so P is not exchanged per epoch at all (finalize() gathers the user ranges once, at the
+        # end); the item deltas of the epoch are summed over the ranks in place:
+        #   Q <- Q - Q_start (local delta), all-reduce, Q <- Q_start + sum of deltas, Q_start <- Q
+        if getattr(self, "_q_start", None) is None:
+            raise RuntimeError("ShardedSGD sgd mode: call begin() once before the first epoch")
         self.accumulate(self.lo, self.hi)
-        dq = self.Q - q0
-        self.dist.all_reduce(dq)
-        self.Q.copy_(q0.add_(dq))
-        if b0 is not None:
-            db = self.Qb - b0
-            self.dist.all_reduce(db)
-            self.Qb.copy_(b0.add_(db))
-        for r in range(self.world):
-            lo, hi = self.bounds[r], self.bounds[r + 1]
-            if hi > lo:
-                self.dist.broadcast(self.P[lo:hi], src=r)
+        self.Q.sub_(self._q_start)
+        self.dist.all_reduce(self.Q)
+        self.Q.add_(self._q_start)
+        self._q_start.copy_(self.Q)
+        if self.Qb is not None:
+            self.Qb.sub_(self._b_start)
+            self.dist.all_reduce(self.Qb)
+            self.Qb.add_(self._b_start)
+            self._b_start.copy_(self.Qb)
         self.apply()
+
+    def begin(self):
+        """sgd mode, world > 1: snapshot of the item side the epoch deltas are taken against."""
+        if self.world > 1 and self.mode == "sgd":
+            self._q_start = self.Q.clone()
+            self._b_start = self.Qb.clone() if self.Qb is not None else None
+
+    def finalize(self):
+        """sgd mode, world > 1: every user range is broadcast from its owner (once, after the last epoch; callers that
+        evaluate between epochs call it before they read rows of P they do not own)."""
+        if self.world > 1 and self.mode == "sgd":
+            for r in range(self.world):
+                lo, hi = self.bounds[r], self.bounds[r + 1]
+                if hi > lo:
+                    self.dist.broadcast(self.P[lo:hi], src=r)
