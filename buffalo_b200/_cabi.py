@@ -80,6 +80,11 @@ PROTOTYPES = {
     # evaluation top-k
     "bfl_topk_device": (C.c_int, [_vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "bfl_topk_host": (C.c_int, [_vp, _i64, C.c_int, _vp, _i64, C.c_int, _vp, C.c_int, C.c_int, _vp, _vp]),
+    # ingest helpers
+    "bfl_csr_from_triples_device": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, C.c_int, _vp, _vp, _vp, _vp]),
+    "bfl_csr_from_triples_host": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, C.c_int, _vp, _vp, _vp]),
+    "bfl_popularity_table_device": (C.c_int, [_vp, _i64, _i32, C.c_int, _vp, _vp]),
+    "bfl_popularity_table_host": (C.c_int, [_vp, _i64, _i32, C.c_int, _vp]),
 }
 
 

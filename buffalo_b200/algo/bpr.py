@@ -89,9 +89,13 @@ class BPRMF(SGDTrainerMixin, Algo, BPRMFOption, Evaluable, Serializable):
         if self.opt.sampling_power > 0.0:
             grp = self.data.get_group("rowwise")
             nnz = int(grp["indptr"][-1]) if len(grp["indptr"]) else 0
-            table = np.bincount(grp["key"][:nnz], minlength=n_items).astype(np.int64)
-            table **= int(self.opt.sampling_power)
-            table = np.cumsum(table).astype(np.int64)
+            from buffalo_b200 import backend
+            if backend.device_available():   # histogram + integer power + scan on the device (csrc/ingest.cu)
+                table = backend.popularity_table_host(grp["key"][:nnz], n_items, int(self.opt.sampling_power))
+            else:
+                table = np.bincount(grp["key"][:nnz], minlength=n_items).astype(np.int64)
+                table **= int(self.opt.sampling_power)
+                table = np.cumsum(table).astype(np.int64)
         self.sampling_table_ = table
         self.obj.set_cumulative_table(self.sampling_table_, n_items)
 

@@ -344,3 +344,28 @@ def topk_device(queries, items, item_bias, k, stream=None):
                                             int(min(queries.shape[1], items.shape[1])), k, idx.data_ptr(), val.data_ptr(),
                                             _stream_ptr(stream)), "bfl_topk_device")
     return idx, val
+
+
+def csr_from_triples_host(major, minor, vals, num_major, num_minor, sort_minor=True):
+    """(indptr_end int64, key int32, val float32) of one orientation through the hand-written device radix sort
+    (csrc/ingest.cu: bfl_csr_from_triples_host)."""
+    mj = np.ascontiguousarray(major, dtype=np.int32)
+    mn = np.ascontiguousarray(minor, dtype=np.int32)
+    v = np.ascontiguousarray(vals, dtype=np.float32)
+    n = len(mj)
+    indptr = np.empty(int(num_major), dtype=np.int64)
+    key = np.empty(max(n, 1), dtype=np.int32)
+    val = np.empty(max(n, 1), dtype=np.float32)
+    _cabi.check(_cabi.lib().bfl_csr_from_triples_host(mj.ctypes.data, mn.ctypes.data, v.ctypes.data, n, int(num_major),
+                                                      int(max(num_minor, 1)), int(bool(sort_minor)), indptr.ctypes.data,
+                                                      key.ctypes.data, val.ctypes.data), "bfl_csr_from_triples_host")
+    return indptr, key[:n], val[:n]
+
+
+def popularity_table_host(keys, n_items, power):
+    """int64 cumulative table of count(item)**power (bpr.py:99-111) built on the device."""
+    k = np.ascontiguousarray(keys, dtype=np.int32)
+    cum = np.empty(int(n_items), dtype=np.int64)
+    _cabi.check(_cabi.lib().bfl_popularity_table_host(k.ctypes.data, len(k), int(n_items), int(power), cum.ctypes.data),
+                "bfl_popularity_table_host")
+    return cum

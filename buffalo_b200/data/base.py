@@ -2,8 +2,8 @@
 (buffalo/data/base.py).  Layout contract kept bit-for-bit (base.py:187-192, fileio.hpp:330-378): per
 orientation `indptr` int64[rows] = exclusive END offsets, `key` int32[nnz] zero-based, `val` float32[nnz],
 rows sorted by (row, col) resp. (col, row), duplicates kept.  The reference's text -> temp files -> parallel
-sort -> HDF5 pipeline is replaced by an in-memory build: NumPy on the host, or one device radix sort (torch) when a
-GPU is present and the matrix is large."""
+sort -> HDF5 pipeline is replaced by an in-memory build: NumPy on the host, or the hand-written device radix sort of
+csrc/ingest.cu when a GPU is present and the matrix is large."""
 import os
 
 import numpy as np
@@ -43,6 +43,11 @@ def csr_from_triples(major, minor, vals, num_major, stable_sort=True, device=Non
                 device = "cuda"
         except ImportError:
             pass
+    if device is not None and str(device).startswith("cuda"):
+        # hand-written device radix sort (csrc/ingest.cu); indices must fit the int32 layout the CSR uses anyway
+        from buffalo_b200 import backend
+        num_minor = int(np.max(minor)) + 1 if len(minor) else 1
+        return backend.csr_from_triples_host(major, minor, vals, num_major, num_minor, sort_minor=stable_sort)
     if device is not None:
         return _csr_from_triples_torch(major, minor, vals, num_major, stable_sort, device)
     if stable_sort:

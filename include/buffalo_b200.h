@@ -230,6 +230,25 @@ int bfl_topk_device(const float* d_queries, int64_t nq, int ldq, const float* d_
 int bfl_topk_host(const float* queries, int64_t nq, int ldq, const float* items, int64_t n_items, int ldi,
                   const float* item_bias /* nullable */, int d, int k, int32_t* out_idx, float* out_val);
 
+/* =====================================================================================
+ * Ingest helpers.
+ * CSR of one orientation from (major, minor, value) triples, the sort/compress stage of
+ * MatrixMarket.create -> _sort_and_compressed_binarization (buffalo/data/mm.py:236-279,
+ * buffalo/data/fileio.hpp:263-419): stable sort by (major, minor) (sort_minor = 0: by major only,
+ * Stream's token order), indptr[num_major] = exclusive END offsets (buffalo/data/base.py:187-192).
+ * Cumulative popularity table of BPRMF.prepare_sampling (buffalo/algo/bpr.py:99-111):
+ * cum[i] = sum_{j<=i} count(j)^power.
+ * ===================================================================================== */
+int bfl_csr_from_triples_device(const int32_t* d_major, const int32_t* d_minor, const float* d_vals, int64_t nnz,
+                                int32_t num_major, int32_t num_minor, int sort_minor, int64_t* d_indptr,
+                                int32_t* d_key_out, float* d_val_out, void* stream);
+int bfl_csr_from_triples_host(const int32_t* major, const int32_t* minor, const float* vals, int64_t nnz,
+                              int32_t num_major, int32_t num_minor, int sort_minor, int64_t* indptr,
+                              int32_t* key_out, float* val_out);
+int bfl_popularity_table_device(const int32_t* d_keys, int64_t nnz, int32_t n_items, int power, int64_t* d_cum,
+                                void* stream);
+int bfl_popularity_table_host(const int32_t* keys, int64_t nnz, int32_t n_items, int power, int64_t* cum);
+
 #ifdef __cplusplus
 }
 #endif

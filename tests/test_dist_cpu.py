@@ -153,8 +153,10 @@ def _sgd_worker(rank, world, port, out, kind, optimizer):
         o.add_jobs(a, b, indptr, np.ascontiguousarray(keys[beg:int(indptr[b - 1])]))
     drv = ShardedSGD(accumulate, o.update_parameters, tP, tQ, tQb, indptr, rank, world, dist, grads=grads)
     assert (drv.lo, drv.hi) == (lo, hi)
+    drv.begin()
     for _ in range(3):
         drv.epoch()
+    drv.finalize()      # sgd mode: the user ranges are gathered once, after the last epoch
     gathered = [torch.zeros_like(tQ) for _ in range(world)]
     dist.all_gather(gathered, tQ)
     out[rank] = dict(same=bool(all(torch.equal(g, gathered[0]) for g in gathered)),
