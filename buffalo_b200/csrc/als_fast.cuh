@@ -546,8 +546,12 @@ struct FastBins {
     DevBuf<int32_t> items;
     DevBuf<unsigned long long> item_counter;
     int64_t n_items = -1;
+    int items_split_class = -1;
 };
-constexpr int64_t TC_SPLIT = 8192;   // nnz per chunk of a split row
+// nnz per chunk of a split row.  The tensor core's fp32 accumulator truncates (measured: -0.5 ulp per accumulating MMA on
+// average, 3 MMAs per 8 entries => ~1.1e-5 relative after 1000 entries), so no accumulator is allowed to run longer
+// than ~2000 entries: longer rows are summed from 2048-entry partial matrices with ordinary rounded fp32 adds.
+constexpr int64_t TC_SPLIT = 2048;
 struct FastBinKey {
     const void* indptr; int64_t b, e;
     bool operator<(const FastBinKey& o) const {
@@ -589,10 +593,11 @@ int fast_launch_class(const AlsArgs& a, int cap, int num_sms, cudaStream_t st) {
 
 // bins rows [row_begin,row_end) of a.indptr by length (cached per (indptr,row range)) and launches one
 // kernel per non-empty class; class 7 (n > FAST_NR_CAP) is returned to the caller through `leftover`.
-// tc_min_class <= 7: classes >= tc_min_class (including 7, rows of any length) are solved by ONE launch of the
-// tensor-core kernel (als_tc.cuh) over their contiguous part of the binned list.
+// Tensor-core kernel (als_tc.cuh): classes tc_min_class .. split_min_class-1 are solved by ONE fused launch over their
+// contiguous part of the binned list; classes >= split_min_class (rows of any length) go through the split-row mode
+// (chunk matrices summed in global memory + explicit-matrix solve).  FAST_NCLASS disables either.
 inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cudaStream_t st,
-                           const int32_t** leftover_rows, int64_t* leftover_count, int tc_min_class,
+                           const int32_t** leftover_rows, int64_t* leftover_count, int tc_min_class, int split_min_class,
                            int long_regather = 0) {
     *leftover_rows = nullptr;
     *leftover_count = 0;
@@ -624,12 +629,13 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
     } else {
         fb = it->second;
     }
-    if (tc_min_class < FAST_NCLASS && fb->count[FAST_NCLASS - 1]) {
-        // rows beyond FAST_NR_CAP (any length): cut into chunks spread over the SMs, partial matrices summed in global
-        // memory, then the explicit-matrix solve
-        const int64_t n7 = fb->count[FAST_NCLASS - 1];
-        const int32_t* list7 = fb->lists.p + fb->offset[FAST_NCLASS - 1];
-        if (fb->n_items < 0) {
+    tc_min_class = std::min(tc_min_class, split_min_class);
+    if (split_min_class < FAST_NCLASS && fb->offset[FAST_NCLASS] > fb->offset[split_min_class]) {
+        // long rows (any length): cut into chunks spread over the SMs, partial matrices summed in global memory, then the
+        // explicit-matrix solve
+        const int64_t n7 = fb->offset[FAST_NCLASS] - fb->offset[split_min_class];
+        const int32_t* list7 = fb->lists.p + fb->offset[split_min_class];
+        if (fb->n_items < 0 || fb->items_split_class != split_min_class) {
             if (BFL_OK != fb->item_counter.reserve(2)) return BFL_ERR_CUDA;
             BFL_CUDA(cudaMemsetAsync(fb->item_counter.p, 0, 2 * sizeof(unsigned long long), st));
             const int g7 = (int)std::min<int64_t>((n7 + 127) / 128, 1024);
@@ -642,6 +648,7 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
             tc::tc_fill_items_kernel<<<g7, 128, 0, st>>>(a0.indptr, list7, n7, TC_SPLIT, fb->item_counter.p + 1, fb->items.p);
             BFL_LAUNCHED();
             fb->n_items = (int64_t)total;
+            fb->items_split_class = split_min_class;
         }
         const size_t sf = a0.D == 128 ? tc::scratch_floats<128>() : tc::scratch_floats<256>();
         if (BFL_OK != cache.scratch.reserve(sf * (size_t)n7)) return BFL_ERR_CUDA;
@@ -660,11 +667,11 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         else als_explicit_solve_kernel<256><<<ge, 256, 0, st>>>(ea);
         BFL_LAUNCHED();
     }
-    if (tc_min_class < FAST_NCLASS - 1 && fb->offset[FAST_NCLASS - 1] > fb->offset[tc_min_class]) {
+    if (tc_min_class < split_min_class && fb->offset[split_min_class] > fb->offset[tc_min_class]) {
         AlsArgs a = a0;
         a.row_list = fb->lists.p;
         a.row_begin = fb->offset[tc_min_class];
-        a.row_end = fb->offset[FAST_NCLASS - 1];
+        a.row_end = fb->offset[split_min_class];
         const int rc = tc::tc_launch(a, num_sms, st);
         if (rc != BFL_OK) return rc;
     }
@@ -694,7 +701,7 @@ inline int fast_als_launch(const AlsArgs& a0, FastCache& cache, int num_sms, cud
         }
         if (rc != BFL_OK) return rc;
     }
-    if (tc_min_class >= FAST_NCLASS && fb->count[FAST_NCLASS - 1]) {
+    if (split_min_class >= FAST_NCLASS && fb->count[FAST_NCLASS - 1]) {
         *leftover_rows = fb->lists.p + fb->offset[FAST_NCLASS - 1];
         *leftover_count = fb->count[FAST_NCLASS - 1];
     }

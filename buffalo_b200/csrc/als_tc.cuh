@@ -12,8 +12,9 @@
 //   producer warp   : walks its rows, one 512-byte cp.async.bulk (TMA, SASS UBLKCP) per gathered opposite-factor
 //                     row into a ring of raw fp32 tiles (32 rows), completion by mbarrier expect_tx;
 //   4 convert warps : raw tile -> s = sqrt|w| q, split into a tf32 head and tail (3xTF32: hi.hi + hi.lo + lo.hi carries
-//                     ~2^-22 relative error, i.e. fp32-grade), written as MN-major unswizzled operand slabs; they also
-//                     accumulate b = sum w q (exact fp32) and the loss pieces;
+//                     ~2^-22 relative error, i.e. fp32-grade), written as MN-major operand slabs in the only layout
+//                     tcgen05 takes for MN-major tf32 (128-byte swizzle with 32-byte atomicity: rows of 32 columns, 4 k
+//                     per atom); they also accumulate b = sum w q (exact fp32) and the loss pieces;
 //   MMA warp        : one lane issues tcgen05.mma kind::tf32 (M = N = 128, K = 8; SASS UTCHMMA), accumulating the row's
 //                     matrix in tensor memory; entries with negative weight travel in their own tiles and are
 //                     subtracted with the instruction descriptor's negate-A bit;
@@ -46,42 +47,44 @@ template <int D>
 struct Cfg {
     static constexpr int TILE = D == 128 ? 32 : 16;      // gathered rows per stage
     static constexpr int NACC = D == 128 ? 3 : 1;        // accumulator sets in tensor memory
-    static constexpr int CG = 128 / TILE;                 // convert threads per gathered row (column groups)
-    static constexpr int CPT = (D / 4) / CG;              // 16-byte column chunks per convert thread (8)
+    static constexpr int KG = TILE / 4;                   // groups of 4 gathered rows (one swizzle atom deep)
+    static constexpr int JS = 16 / KG;                    // column-chunk selectors per (k, chunk parity)
+    static constexpr int NPART = D == 128 ? 2 : 1;        // partial b vectors handed to the epilogue (summed there)
     static constexpr int KSTEP_FLOATS = 8 * D;            // one K = 8 slab of an operand array
 };
 constexpr int NACC_MAX = 3;
+constexpr uint64_t SWZ_128B_BASE32B = 1ull << 61;   // matrix-descriptor layout type 1
 constexpr uint32_t F_FIRST = 1u << 8, F_LAST = 1u << 9, F_NEG = 1u << 10, F_STOP = 1u << 11;
 
 template <int D>
 struct Smem {
-    static constexpr int RAWP = D + 4;                 // floats; 16-byte pad: conflict-free 128-bit reads down a column
+    static constexpr int RAWP = D + 8;                 // floats; 32-byte pad: conflict-free 128-bit reads of the convert map
     static constexpr int TILE = Cfg<D>::TILE;
-    float raw[NR][TILE * RAWP];
-    float op[NO][2][TILE * D];                         // [hi|lo][k-step][D/4 chunks][8][4]
-    float bvec[NBV][D];                                // b = sum w q
-    float sumq[NBV][D];                                // sum q (loss only)
-    float wsum[NBV];                                   // sum w (loss only)
-    float sw[NR][TILE];                                // sign(w) sqrt|w| per slot
+    alignas(1024) float op[NO][2][TILE * D];           // [hi|lo][k-step slab]: swizzled MN-major atoms (see op_offset)
+    alignas(128) float raw[NR][TILE * RAWP];
+    alignas(16) float bvec[NBV][Cfg<D>::NPART][D];     // b = sum w q (partials over the convert warps)
+    alignas(16) float sumq[NBV][Cfg<D>::NPART][D];     // sum q (loss only)
+    alignas(16) float xs[2][D];                        // 128-bit reads: every vector below is 16-byte aligned
+    alignas(16) float pv[2][32];
+    alignas(16) float dl[2][2][32];
+    alignas(16) float sw[NR][TILE];                    // sign(w) sqrt|w| per slot
+    float wsum[NBV][2];                                // sum w (loss only; partials)
     uint32_t meta_raw[NR];
     uint32_t meta_op[NO];
-    float xs[2][D];
-    float pv[2][32];
-    float dl[2][2][32];
     int badf[2][4];
-    uint64_t raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO], acc_full[NACC_MAX], acc_empty[NACC_MAX];
+    alignas(8) uint64_t raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO], acc_full[NACC_MAX], acc_empty[NACC_MAX];
     uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
-// sums v[i] (32 values per lane) over groups of NL consecutive lanes; afterwards lane l of a group holds the totals
-// of indices (32/NL) * l + e in v[e], e < 32/NL
-template <int NL>
-__device__ __forceinline__ void transpose_reduce(float (&v)[32], int lane) {
+// sums v[i] (32 values per lane) over the 16 lanes that share lane bit 2 (xor offsets 16, 8, 2, 1); afterwards a lane
+// holds in v[0], v[1] the totals of indices (b4 << 4 | b3 << 3 | b1 << 2 | b0 << 1) + {0, 1}, b_x = bit x of the lane id
+__device__ __forceinline__ void transpose_reduce16(float (&v)[32], int lane) {
     int nv = 32;
 #pragma unroll
-    for (int off = NL / 2; off >= 1; off >>= 1) {
+    for (int s = 0; s < 4; ++s) {
+        const int off = s == 0 ? 16 : (s == 1 ? 8 : (s == 2 ? 2 : 1));
         nv >>= 1;
         const bool up = lane & off;
 #pragma unroll
@@ -113,7 +116,7 @@ template <int D, bool PARTIAL>
 __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
     static_assert(D == 128 || (D == 256 && PARTIAL), "fused row solve: d = 128; split-row mode: d = 128 or 256");
     constexpr int TILE = Cfg<D>::TILE, NACC = Cfg<D>::NACC, KSTEP_FLOATS = Cfg<D>::KSTEP_FLOATS;
-    extern __shared__ __align__(128) unsigned char smem_raw_[];
+    extern __shared__ __align__(1024) unsigned char smem_raw_[];
     Smem<D>& S = *reinterpret_cast<Smem<D>*>(smem_raw_);
     const AlsArgs& a = ta.a;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -262,8 +265,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 const uint32_t hi = s32(&S.op[os][0][0]), lo = s32(&S.op[os][1][0]);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint32_t acc0 = (row_open || ks > 0) ? 1u : 0u;
-                    const uint64_t dh = smem_desc(hi + ks * KSTEP_FLOATS * 4, KSTEP_FLOATS * 4, 128);
-                    const uint64_t dl = smem_desc(lo + ks * KSTEP_FLOATS * 4, KSTEP_FLOATS * 4, 128);
+                    // MN-major tf32 operand: SWIZZLE_128B_BASE32B atoms of 32 (M/N) x 4 (K) values = 512 B; the next 4 k
+                    // 512 B further (stride-dimension offset), the next 32 columns 1024 B further (leading-dimension offset)
+                    const uint64_t dh = smem_desc(hi + ks * KSTEP_FLOATS * 4, 1024, 512) | SWZ_128B_BASE32B;
+                    const uint64_t dl = smem_desc(lo + ks * KSTEP_FLOATS * 4, 1024, 512) | SWZ_128B_BASE32B;
                     if (D == 128) {
                         const uint32_t dcol = tmem + D * (1 + acc);
                         mma_tf32(dcol, dh, dh, id, acc0);
@@ -276,8 +281,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         mma_tf32(tmem, dh, dl, idw, 1u);
                         mma_tf32(tmem, dl, dh, idw, 1u);
                         // rows 128..255 x columns 128..255 -> tensor-memory columns [256, 384): the slab's second half
-                        const uint64_t eh = smem_desc(hi + ks * KSTEP_FLOATS * 4 + 4096, KSTEP_FLOATS * 4, 128);
-                        const uint64_t el = smem_desc(lo + ks * KSTEP_FLOATS * 4 + 4096, KSTEP_FLOATS * 4, 128);
+                        const uint64_t eh = smem_desc(hi + ks * KSTEP_FLOATS * 4 + 4096, 1024, 512) | SWZ_128B_BASE32B;
+                        const uint64_t el = smem_desc(lo + ks * KSTEP_FLOATS * 4 + 4096, 1024, 512) | SWZ_128B_BASE32B;
                         mma_tf32(tmem + 256, eh, eh, id, acc0);
                         mma_tf32(tmem + 256, eh, el, id, 1u);
                         mma_tf32(tmem + 256, el, eh, id, 1u);
@@ -295,9 +300,18 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         }
     } else if (warp >= W_CONV && warp < W_CONV + N_CONV) {
         // ================= convert: raw fp32 -> scaled tf32 head/tail operand slabs =================
+        // thread -> gathered row k = 4*kg + k4 of the tile and the 16-byte column chunks j = jpar + 2*(jsel + JS*i).
+        // lane bits 0-1 = k % 4 and bit 2 = chunk parity make every quarter-warp hit 8 distinct 16-byte bank groups,
+        // both on the raw read (pitch D+8 floats) and on the swizzled operand write.
         const int ct = tid - W_CONV * 32;
-        const int k = ct % TILE, cg = ct / TILE;   // gathered row of the tile, column group
-        constexpr int CG = Cfg<D>::CG, CPT = Cfg<D>::CPT;
+        constexpr int KG = Cfg<D>::KG, JS = Cfg<D>::JS, NPART = Cfg<D>::NPART;
+        const int k4 = ct & 3, jpar = (ct >> 2) & 1, rest = ct >> 3;
+        const int kg = rest % KG, jsel = rest / KG;
+        const int k = 4 * kg + k4;
+        const int part = NPART == 2 ? ((ct >> 5) & 1) : 0;          // which half of the k groups this warp covers
+        // element (k, column m = 4j..4j+3) of a K = 8 slab, in floats:
+        //   (m/32)*256 + ((k%8)/4)*128 + (k%4)*32 + ((((m%32)/8) ^ (k%4))*8) + m%8
+        const int op_base = (k >> 3) * KSTEP_FLOATS + ((k >> 2) & 1) * 128 + k4 * 32 + jpar * 4;
         uint32_t rs = 0, rph = 0, os = 0, oph = 0, bslot = 0;
         float bacc[32], qacc[32];
         float wacc = 0.f;
@@ -322,21 +336,22 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 const bool valid = k < cnt;
                 const float swv = valid ? S.sw[rs][k] : 0.f;
                 const float sa = fabsf(swv);
-                if (cg == 0) wacc = fmaf(swv, sa, wacc);   // cg == 0 lives in the first convert warp (lanes < TILE)
-                float* hi = &S.op[os][0][(k >> 3) * KSTEP_FLOATS + (k & 7) * 4];
-                float* lo = &S.op[os][1][(k >> 3) * KSTEP_FLOATS + (k & 7) * 4];
+                if (jpar == 0 && jsel == 0) wacc = fmaf(swv, sa, wacc);
+                float* hi = &S.op[os][0][op_base];
+                float* lo = &S.op[os][1][op_base];
                 const float* rp = &S.raw[rs][k * RAWP];
 #pragma unroll
-                for (int i = 0; i < CPT; ++i) {
-                    const int j = cg + CG * i;   // 16-byte column chunk
+                for (int i = 0; i < 8; ++i) {
+                    const int j = jpar + 2 * (jsel + JS * i);   // 16-byte column chunk
+                    const int o = (j >> 3) * 256 + ((((j & 7) >> 1) ^ k4) * 8);
                     float4 q = valid ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 s = make_float4(q.x * sa, q.y * sa, q.z * sa, q.w * sa), h, l;
                     split_tf32(s.x, h.x, l.x);
                     split_tf32(s.y, h.y, l.y);
                     split_tf32(s.z, h.z, l.z);
                     split_tf32(s.w, h.w, l.w);
-                    *reinterpret_cast<float4*>(hi + j * 32) = h;
-                    *reinterpret_cast<float4*>(lo + j * 32) = l;
+                    *reinterpret_cast<float4*>(hi + o) = h;
+                    *reinterpret_cast<float4*>(lo + o) = l;
                     bacc[4 * i + 0] = fmaf(swv, s.x, bacc[4 * i + 0]);
                     bacc[4 * i + 1] = fmaf(swv, s.y, bacc[4 * i + 1]);
                     bacc[4 * i + 2] = fmaf(swv, s.z, bacc[4 * i + 2]);
@@ -349,20 +364,20 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             fence_proxy_async_smem();
             mbar_arrive(&S.raw_empty[rs]);
             if (meta & F_LAST) {
-                // value index 4*i + comp (chunk cg + CG*i, component comp); after the reduction over the TILE lanes that
-                // share cg, lane l of the group holds indices (32/TILE)*l + e
-                transpose_reduce<TILE>(bacc, lane);
-                if (ta.loss_axis1) transpose_reduce<TILE>(qacc, lane);
+                // value index 4*i + comp <-> column 4*j(i) + comp; the 16 lanes sharing (jpar, jsel) are reduced
+                transpose_reduce16(bacc, lane);
+                if (ta.loss_axis1) transpose_reduce16(qacc, lane);
+                const int vi0 = ((lane >> 4) & 1) << 4 | ((lane >> 3) & 1) << 3 | ((lane >> 1) & 1) << 2 | (lane & 1) << 1;
 #pragma unroll
-                for (int e = 0; e < 32 / TILE; ++e) {
-                    const int vi = (32 / TILE) * (lane % TILE) + e;
-                    const int col = 4 * (cg + CG * (vi >> 2)) + (vi & 3);
-                    S.bvec[bslot][col] = bacc[e];
-                    if (ta.loss_axis1) S.sumq[bslot][col] = qacc[e];
+                for (int e = 0; e < 2; ++e) {
+                    const int vi = vi0 + e;
+                    const int col = 4 * (jpar + 2 * (jsel + JS * (vi >> 2))) + (vi & 3);
+                    S.bvec[bslot][part][col] = bacc[e];
+                    if (ta.loss_axis1) S.sumq[bslot][part][col] = qacc[e];
                 }
-                if (ta.loss_axis1 && warp == W_CONV) {   // the first convert warp sees every gathered row (k) of the tile
-                    const float ws = warp_sum(lane < TILE ? wacc : 0.f);
-                    if (lane == 0) S.wsum[bslot] = ws;
+                if (ta.loss_axis1 && jsel == 0) {   // warps whose threads (jpar == 0) see each gathered row once
+                    const float ws = warp_sum(jpar == 0 ? wacc : 0.f);
+                    if (lane == 0) S.wsum[bslot][part] = ws;
                 }
                 bslot = (bslot + 1) & (NBV - 1);
             }
@@ -437,10 +452,17 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     }
                 }
                 for (int jj = j; jj < D; jj += 128) {
-                    atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][jj]);
-                    if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
+                    float bb = 0.f, qq = 0.f;
+#pragma unroll
+                    for (int pp = 0; pp < Cfg<D>::NPART; ++pp) {
+                        bb += S.bvec[bs][pp][jj];
+                        if (ta.loss_axis1) qq += S.sumq[bs][pp][jj];
+                    }
+                    atomicAdd(sc + (size_t)D * D + jj, bb);
+                    if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, qq);
                 }
-                if (ta.loss_axis1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
+                if (ta.loss_axis1 && j == 0)
+                    atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs][0] + (Cfg<D>::NPART == 2 ? S.wsum[bs][1] : 0.f));
                 tc_fence_before();
                 mbar_arrive(&S.acc_empty[acc]);
                 row = nrow; slot = nslot; n = nn;
@@ -448,7 +470,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
             const uint32_t dbase = tmem + lane_off + 128 * (1 + acc);
             xs[j] = xj;
-            const float bj = S.bvec[bs][j];
+            float bj = S.bvec[bs][0][j];
+            if (Cfg<D>::NPART == 2) bj += S.bvec[bs][Cfg<D>::NPART - 1][j];
             group_sync(g);
             // ---- h = (G + reg I) x + D x - b; keep the diagonal block of M in registers ----
             float hG = 0.f, hD = 0.f;
@@ -482,10 +505,12 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 double t = (double)(kappa * a.reg * xj * xj);
                 if (a.axis == 1) {
                     t += (double)xj * (double)(hG - a.reg * xj) + (double)xj * (double)hD -
-                         2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][j]);
+                         2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][0][j] +
+                                             (Cfg<D>::NPART == 2 ? (double)S.sumq[bs][Cfg<D>::NPART - 1][j] : 0.0));
                     if (j == 0) {
-                        t += (double)n + (double)S.wsum[bs];
-                        l_deno += (double)a.Y_rows + (double)S.wsum[bs];
+                        const double ws = (double)S.wsum[bs][0] + (Cfg<D>::NPART == 2 ? (double)S.wsum[bs][1] : 0.0);
+                        t += (double)n + ws;
+                        l_deno += (double)a.Y_rows + ws;
                     }
                 }
                 l_nume += t;
