@@ -334,7 +334,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (tuned SIMT kernels), 1 generic kernels, 3 tensor-core Gram variant")
+    ap.add_argument("--kernel-mode", type=int, default=0, help="0 auto (d=128: tcgen05 kernel + SIMT class 0), 1 generic kernels, 2 tuned SIMT kernels only")
+    ap.add_argument("--tc-min-class", type=int, default=None, help="first row-length class solved by the tensor-core kernel (default: library's)")
     ap.add_argument("--exchange", default=os.environ.get("BFL_EXCHANGE", "p2p"), choices=["p2p", "allgather"],
                     help="multi-GPU: fused peer stores from the solve kernel (default) or an NCCL all-gather per half-epoch")
     args = ap.parse_args()
@@ -355,6 +356,8 @@ def main():
     w = WORKLOADS[args.workload]
     d = w["d"]
     opt = dict(ALS_OPT, d=d, _b200_kernel_mode=args.kernel_mode)
+    if args.tc_min_class is not None:
+        opt["_b200_tc_min_class"] = args.tc_min_class
     cores, tinfo = host_threads()
 
     if args.impl == "reference":

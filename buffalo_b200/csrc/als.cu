@@ -47,6 +47,13 @@ struct bfl_als {
     DevBuf<float> yui;        // generic ialspp scratch
     DevBuf<double> d_loss;    // 2 doubles
     FastCache fast_cache;     // row-length bins of the tuned path, keyed by (indptr, row range)
+    // tensor-core path (als_tc.cuh): max|Y| (noted by precompute, which reads the whole opposite factor anyway) and
+    // max|v| of the launch -> power-of-two operand scale, all on the device
+    DevBuf<unsigned int> tc_maxes;   // [0] bits of max|Y|, [1 + axis] bits of max|v| of that orientation's values
+    DevBuf<float> tc_scales;         // [0] 2^e, [1] 2^-2e
+    bool tc_on = false;
+    const float* tc_vals_seen[2] = {nullptr, nullptr};   // resident CSR: max|v| is noted once per bound value array
+    int64_t tc_vals_seen_n[2] = {0, 0};
     int n_peer[2] = {0, 0};   // fused multi-GPU exchange targets per axis
     float* peers[2][BFL_MAX_PEERS] = {};
     cudaStream_t stream = nullptr;
@@ -95,8 +102,22 @@ int als_apply_options(bfl_als* h, const JsonOpt& j) {
     }
     if (BFL_OK != h->G.reserve((size_t)h->d * h->d)) return BFL_ERR_CUDA;
     if (BFL_OK != h->d_loss.reserve(2)) return BFL_ERR_CUDA;
+    h->tc_on = h->kernel_mode == 0 && tc::tc_split_applicable(h->optimizer_code, h->d, h->vdim, h->block_size);
+    if (h->tc_on) {
+        if (BFL_OK != h->tc_maxes.reserve(3) || BFL_OK != h->tc_scales.reserve(2)) return BFL_ERR_CUDA;
+        BFL_CUDA(cudaMemsetAsync(h->tc_maxes.p, 0, 3 * sizeof(unsigned int), h->stream));
+    }
+    h->tc_vals_seen[0] = h->tc_vals_seen[1] = nullptr;
     h->opt_set = true;
     return BFL_OK;
+}
+
+// max|Y| over the WHOLE opposite factor of `axis` (the tensor-core kernel's operand scale)
+int note_factor_absmax(bfl_als* h, int axis, cudaStream_t st) {
+    if (!h->tc_on) return BFL_OK;
+    const float* F = axis == 0 ? h->dQ : h->dP;
+    const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
+    return tc::tc_note_absmax(F, (size_t)rows * h->vdim, h->tc_maxes.p, h->num_sms, st);
 }
 
 int gram(bfl_als* h, const float* F, int64_t rows, cudaStream_t st) {
@@ -157,7 +178,20 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
     a.tol = h->cg_tolerance;
     a.n_peer = h->n_peer[axis];
     for (int i = 0; i < BFL_MAX_PEERS; ++i) a.peerX[i] = i < a.n_peer ? h->peers[axis][i] : nullptr;
+    a.tc_scales = nullptr;
     int64_t nrows = row_end - row_begin;
+    if (h->tc_on) {
+        // max|v| of this launch's values (a resident array is scanned once), then the operand scale -- device only
+        if (vals != h->tc_vals_seen[axis] || chunk_nnz != h->tc_vals_seen_n[axis]) {
+            int rc = tc::tc_note_absmax(vals, (size_t)std::max<int64_t>(chunk_nnz, 0), h->tc_maxes.p + 1 + axis, h->num_sms, st);
+            if (rc != BFL_OK) return rc;
+            h->tc_vals_seen[axis] = vals == h->d_vals[axis] ? vals : nullptr;   // staged host chunks: scanned every time
+            h->tc_vals_seen_n[axis] = chunk_nnz;
+        }
+        int rc = tc::tc_update_scale(h->tc_maxes.p, h->tc_maxes.p + 1 + axis, h->alpha, h->tc_scales.p, st);
+        if (rc != BFL_OK) return rc;
+        a.tc_scales = h->tc_scales.p;
+    }
 
     if (h->kernel_mode != 1 && fast_als_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
         const int32_t* left = nullptr;
@@ -292,6 +326,8 @@ int bfl_als_precompute(bfl_als_t* h, int axis) {
     const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
     int rc = gram(h, F, rows, h->stream);
     if (rc != BFL_OK) return rc;
+    rc = note_factor_absmax(h, axis, h->stream);
+    if (rc != BFL_OK) return rc;
     BFL_CUDA(cudaStreamSynchronize(h->stream));
     return BFL_OK;
 }
@@ -404,6 +440,7 @@ int bfl_als_bind_csr_device(bfl_als_t* h, int axis, const int64_t* d_indptr, con
     if (!d_indptr || (nnz > 0 && (!d_keys || !d_vals)) || rows <= 0) BFL_FAIL(BFL_ERR_ARG, "bad CSR arguments");
     h->fast_cache.clear();
     h->indptr_uploaded[axis] = false;
+    h->tc_vals_seen[axis] = nullptr;
     h->d_indptr[axis] = d_indptr;
     h->d_keys[axis] = d_keys;
     h->d_vals[axis] = d_vals;
@@ -417,7 +454,9 @@ int bfl_als_precompute_device(bfl_als_t* h, int axis, void* stream) {
     if (axis != 0 && axis != 1) BFL_FAIL(BFL_ERR_ARG, "axis must be 0 or 1");
     const float* F = axis == 0 ? h->dQ : h->dP;
     const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
-    return gram(h, F, rows, (cudaStream_t)stream);
+    int rc = gram(h, F, rows, (cudaStream_t)stream);
+    if (rc != BFL_OK) return rc;
+    return note_factor_absmax(h, axis, (cudaStream_t)stream);
 }
 
 int bfl_als_precompute_rows_device(bfl_als_t* h, int axis, int64_t row_begin, int64_t row_end, void* stream) {
@@ -426,6 +465,9 @@ int bfl_als_precompute_rows_device(bfl_als_t* h, int axis, int64_t row_begin, in
     const float* F = axis == 0 ? h->dQ : h->dP;
     const int64_t rows = axis == 0 ? h->Q_rows : h->P_rows;
     if (row_begin < 0 || row_end > rows || row_end < row_begin) BFL_FAIL(BFL_ERR_ARG, "bad row range");
+    // the operand scale needs max|Y| of the whole replica, not of the range (every rank gathers from all rows)
+    int rc = note_factor_absmax(h, axis, (cudaStream_t)stream);
+    if (rc != BFL_OK) return rc;
     if (row_end == row_begin) {
         BFL_CUDA(cudaMemsetAsync(h->G.p, 0, sizeof(float) * (size_t)h->d * h->d, (cudaStream_t)stream));
         return BFL_OK;

@@ -31,6 +31,7 @@ struct AlsArgs {
     float alpha, reg, eps, tol;
     int n_peer;           // fused multi-GPU exchange: every solved row is also stored to these replicas of X
     float* peerX[15];
+    const float* tc_scales;  // tensor-core path: [0] operand scale 2^e, [1] 2^-2e (device; null when that path is off)
 };
 constexpr int BFL_MAX_PEERS = 15;
 

@@ -8,14 +8,25 @@
 // fixed 3-step CG on 32 x 32 diagonal blocks -- O(d^2) work per row that does not depend on the row length, and the
 // per-nnz work collapses into one rank-1 update  M += (sqrt(w) q)(sqrt(w) q)^T, a dense contraction: tensor cores.
 //
-// Pipeline of one persistent CTA (one per SM, 14 warps, warp-specialised, mbarrier hand-offs only):
-//   producer warp   : walks its rows, one 512-byte cp.async.bulk (TMA, SASS UBLKCP) per gathered opposite-factor
-//                     row into a ring of raw fp32 tiles (32 rows), completion by mbarrier expect_tx;
-//   4 convert warps : raw tile -> s = sqrt|w| q, split into a tf32 head and tail (3xTF32: hi.hi + hi.lo + lo.hi carries
-//                     ~2^-22 relative error, i.e. fp32-grade), written as MN-major operand slabs in the only layout
-//                     tcgen05 takes for MN-major tf32 (128-byte swizzle with 32-byte atomicity: rows of 32 columns, 4 k
-//                     per atom); they also accumulate b = sum w q (exact fp32) and the loss pieces;
-//   MMA warp        : one lane issues tcgen05.mma kind::tf32 (M = N = 128, K = 8; SASS UTCHMMA), accumulating the row's
+// Precision.  The contraction runs on tcgen05.mma kind::f16 with a two-term fp16 split of the scaled operand
+// t = 2^e sqrt|w| q = head + tail (head: 11 significant bits, tail: the next 11): head.head + head.tail + tail.head
+// leaves a relative error of ~2^-21 per product, fp32-grade like the reference's arithmetic, at twice the tensor rate and
+// half the shared-memory traffic per entry of the equivalent 3xTF32 scheme (K = 16 per instruction instead of 8).  The
+// power of two 2^e (tc_scale_kernel: from max|Y| and max|w| of the launch) places the largest operand just below 2^15, so
+// nothing overflows fp16 and entries down to 2^-20 of the largest keep a normal tail; the accumulator is multiplied by
+// 2^-2e (exact) when it is read.  b and the loss pieces are accumulated in plain fp32 from the unscaled rows.
+//
+// Pipeline of one persistent CTA (one per SM, 16 warps, warp-specialised, mbarrier hand-offs only):
+//   3 producer warps : walk the CTA's rows in lock step; per tile of 32 gathered opposite-factor rows every warp issues a
+//                     third of the 512-byte cp.async.bulk copies (TMA, SASS UBLKCP).  A divergent-address bulk copy
+//                     compiles to an ELECT / R2UR / UBLKCP loop over the lanes, ~63 cycles per copy and warp: one warp
+//                     alone sustains 2.3 TB/s chip-wide, two 4.7, four or more the 7.0 TB/s HBM read ceiling
+//                     (benchmarks/gather_probe.cu); copies land in a ring of raw fp32 tiles, completion by mbarrier
+//                     expect_tx;
+//   4 convert warps  : thread m owns feature m: reads column m of the raw tile (conflict-free), scales, splits, and writes
+//                     16-byte groups of 8 consecutive k into the K-major un-swizzled operand slabs (8 x 16 B core
+//                     matrices); accumulates b_m = sum w q_m (exact fp32) and the loss pieces in registers;
+//   MMA warp         : one lane issues tcgen05.mma kind::f16 (M = N = 128, K = 16; SASS UTCHMMA), accumulating the row's
 //                     matrix in tensor memory; entries with negative weight travel in their own tiles and are
 //                     subtracted with the instruction descriptor's negate-A bit;
 //   2 x 4 epilogue warps : thread j owns matrix row j (tensor-memory lane j): tcgen05.ld (SASS LDTM) the accumulator and
@@ -35,10 +46,13 @@ namespace tc {
 
 using namespace sm100;
 
-constexpr int WARPS = 14, THREADS = WARPS * 32;
-constexpr int W_PROD = 0, W_MMA = 1, W_CONV = 2, N_CONV = 4, W_EPI = 6;   // warps 6..9 group 0, 10..13 group 1
-constexpr int NR = 4;      // raw stages
-constexpr int NO = 3;      // operand stages
+// 16 warps x 128 registers fill the register file (registers are allocated for warp counts rounded up to 4: a 17th warp
+// would cap every thread at 96 registers and spill the epilogue)
+constexpr int N_PROD = 3, N_CONV = 4;
+constexpr int W_PROD = 0, W_MMA = 3, W_CONV = 4, W_EPI = 8;   // warps 8..11 epilogue group 0, 12..15 group 1
+constexpr int WARPS = 16, THREADS = WARPS * 32;
+constexpr int NR = 6;      // raw stages
+constexpr int NO = 4;      // operand stages
 constexpr int NBV = 8;     // ring of per-row vectors handed from the convert warps to the epilogue
 // d = 128: 32 gathered rows per stage, three 128-column accumulators (fused solve) behind the resident G + reg I;
 // d = 256 (split-row mode only): 16 rows per stage, one accumulator set of 384 columns: rows 0..127 x all 256 columns
@@ -47,28 +61,27 @@ template <int D>
 struct Cfg {
     static constexpr int TILE = D == 128 ? 32 : 16;      // gathered rows per stage
     static constexpr int NACC = D == 128 ? 3 : 1;        // accumulator sets in tensor memory
-    static constexpr int KG = TILE / 4;                   // groups of 4 gathered rows (one swizzle atom deep)
-    static constexpr int JS = 16 / KG;                    // column-chunk selectors per (k, chunk parity)
-    static constexpr int NPART = D == 128 ? 2 : 1;        // partial b vectors handed to the epilogue (summed there)
-    static constexpr int KSTEP_FLOATS = 8 * D;            // one K = 8 slab of an operand array
+    static constexpr int NF = D / 128;                    // features per convert thread
+    static constexpr int LBO = D * 16;                    // bytes between the 8-k chunks of an operand slab
+    static constexpr int OP_BYTES = TILE * D * 2;         // head (or tail) slab of one stage
 };
 constexpr int NACC_MAX = 3;
-constexpr uint64_t SWZ_128B_BASE32B = 1ull << 61;   // matrix-descriptor layout type 1
 constexpr uint32_t F_FIRST = 1u << 8, F_LAST = 1u << 9, F_NEG = 1u << 10, F_STOP = 1u << 11;
 
 template <int D>
 struct Smem {
-    static constexpr int RAWP = D + 8;                 // floats; 32-byte pad: conflict-free 128-bit reads of the convert map
     static constexpr int TILE = Cfg<D>::TILE;
-    alignas(1024) float op[NO][2][TILE * D];           // [hi|lo][k-step slab]: swizzled MN-major atoms (see op_offset)
-    alignas(128) float raw[NR][TILE * RAWP];
-    alignas(16) float bvec[NBV][Cfg<D>::NPART][D];     // b = sum w q (partials over the convert warps)
-    alignas(16) float sumq[NBV][Cfg<D>::NPART][D];     // sum q (loss only)
+    // operand slab: element (feature m, entry k) at byte (k/8)*LBO + (m/8)*128 + (m%8)*16 + (k%8)*2
+    alignas(1024) unsigned char op[NO][2][Cfg<D>::OP_BYTES];   // [head|tail]
+    alignas(128) float raw[NR][TILE * D];              // gathered rows, pitch D
+    alignas(16) float bvec[NBV][D];                    // b = sum w q
+    alignas(16) float sumq[NBV][D];                    // sum q (loss only)
     alignas(16) float xs[2][D];                        // 128-bit reads: every vector below is 16-byte aligned
     alignas(16) float pv[2][32];
     alignas(16) float dl[2][2][32];
-    alignas(16) float sw[NR][TILE];                    // sign(w) sqrt|w| per slot
-    float wsum[NBV][2];                                // sum w (loss only; partials)
+    alignas(16) float sws[NR][TILE];                   // 2^e sqrt|w| per slot
+    alignas(16) float wv[NR][TILE];                    // w per slot
+    float wsum[NBV];                                   // sum w (loss only)
     uint32_t meta_raw[NR];
     uint32_t meta_op[NO];
     int badf[2][4];
@@ -77,26 +90,6 @@ struct Smem {
 };
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
-
-// sums v[i] (32 values per lane) over the 16 lanes that share lane bit 2 (xor offsets 16, 8, 2, 1); afterwards a lane
-// holds in v[0], v[1] the totals of indices (b4 << 4 | b3 << 3 | b1 << 2 | b0 << 1) + {0, 1}, b_x = bit x of the lane id
-__device__ __forceinline__ void transpose_reduce16(float (&v)[32], int lane) {
-    int nv = 32;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int off = s == 0 ? 16 : (s == 1 ? 8 : (s == 2 ? 2 : 1));
-        nv >>= 1;
-        const bool up = lane & off;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < nv) {
-                const float send = up ? v[i] : v[i + nv];
-                const float keep = up ? v[i + nv] : v[i];
-                v[i] = keep + __shfl_xor_sync(FULL, send, off);
-            }
-        }
-    }
-}
 
 // PARTIAL = false: rows of a.row_list[row_begin..row_end) are solved in place.
 // PARTIAL = true : the list holds chunk items of long rows (pairs: row, chunk index); the chunk's matrix and vectors are
@@ -112,20 +105,52 @@ struct TcArgs {
 template <int D>
 __host__ __device__ constexpr size_t scratch_floats() { return (size_t)D * D + 2 * D + 4; }
 
+// operand scaling of one launch: out[0] = 2^e, out[1] = 2^-2e with 2^e max|Y| sqrt(max|w|) in [2^14, 2^15)
+__global__ void tc_absmax_kernel(const float* __restrict__ p, size_t n, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+    const size_t lead = min(n, (size_t)(((16 - ((uintptr_t)p & 15)) & 15) / 4));   // scalars up to 16-byte alignment
+    const size_t n4 = (n - lead) / 4;
+    const float4* p4 = reinterpret_cast<const float4*>(p + lead);
+    for (size_t i = gtid; i < n4; i += gsz) {
+        const float4 v = __ldg(p4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (size_t i = gtid; i < lead; i += gsz) m = fmaxf(m, fabsf(p[i]));
+    for (size_t i = lead + n4 * 4 + gtid; i < n; i += gsz) m = fmaxf(m, fabsf(p[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    // non-negative floats order like their bit patterns (fmaxf drops NaNs; an Inf input ends up as scale 2^-60, the rows
+    // it touches come out non-finite and are zeroed by the guard, like the reference's GPU path)
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+__global__ void tc_scale_kernel(const unsigned int* __restrict__ ymax, const unsigned int* __restrict__ vmax, float alpha,
+                                float* __restrict__ out) {
+    const float y = __uint_as_float(*ymax), w = __uint_as_float(*vmax) * fabsf(alpha);
+    const float top = y * sqrtf(w);
+    int e = 0;
+    if (top > 0.f && isfinite(top)) {
+        int ex;
+        frexpf(top, &ex);          // top = f * 2^ex, f in [0.5, 1)
+        e = 15 - ex;               // 2^e top in [2^14, 2^15)
+    }
+    e = max(-60, min(60, e));
+    out[0] = ldexpf(1.f, e);
+    out[1] = ldexpf(1.f, -2 * e);
+}
+
 template <int D, bool PARTIAL>
 __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
     static_assert(D == 128 || (D == 256 && PARTIAL), "fused row solve: d = 128; split-row mode: d = 128 or 256");
-    constexpr int TILE = Cfg<D>::TILE, NACC = Cfg<D>::NACC, KSTEP_FLOATS = Cfg<D>::KSTEP_FLOATS;
+    constexpr int TILE = Cfg<D>::TILE, NACC = Cfg<D>::NACC, NF = Cfg<D>::NF, LBO = Cfg<D>::LBO;
     extern __shared__ __align__(1024) unsigned char smem_raw_[];
     Smem<D>& S = *reinterpret_cast<Smem<D>*>(smem_raw_);
     const AlsArgs& a = ta.a;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(FULL, tid >> 5, 0);
-    constexpr int RAWP = Smem<D>::RAWP;
 
     if (tid == 0) {
         for (int i = 0; i < NR; ++i) {
-            mbar_init(&S.raw_full[i], 1);
+            mbar_init(&S.raw_full[i], N_PROD);
             mbar_init(&S.raw_empty[i], N_CONV * 32);
         }
         for (int i = 0; i < NO; ++i) {
@@ -134,7 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&S.acc_full[i], 1);
-            mbar_init(&S.acc_empty[i], 128);
+            mbar_init(&S.acc_empty[i], NACC == 1 ? 256 : 128);   // one accumulator: both epilogue groups drain it together
         }
         mbar_init_fence();
     }
@@ -143,6 +168,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
+    const float scale = __ldg(a.tc_scales), inv2 = __ldg(a.tc_scales + 1);
 
     // G + reg I -> tensor memory columns [0, D) (epilogue group 0; thread j holds matrix row j)
     if (!PARTIAL && warp >= W_EPI && warp < W_EPI + 4) {
@@ -187,22 +213,29 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         }
     };
 
-    if (warp == W_PROD) {
-        // ================= producer: gathers =================
+    if (warp < W_PROD + N_PROD) {
+        // ================= producers: gathers =================
+        // All producer warps walk the same tile sequence; warp pw issues the copies of the slots with slot % N_PROD == pw.
+        const int pw = warp - W_PROD;
         uint32_t rs = 0, rph = 0;   // stage, phase of raw_empty
         auto emit = [&](unsigned mask, uint32_t flags, int32_t key, float w) {
             const int cnt = __popc(mask);
-            const bool mine = (mask >> lane) & 1u;
             const int slot = __popc(mask & ((1u << lane) - 1u));
+            const bool mine = ((mask >> lane) & 1u) && slot % N_PROD == pw;
+            const int nmine = (cnt + N_PROD - 1 - pw) / N_PROD;
             mbar_wait(&S.raw_empty[rs], rph ^ 1u);
-            if (mine) S.sw[rs][slot] = copysignf(sqrtf(fabsf(w)), w);
+            if (mine) {
+                S.sws[rs][slot] = sqrtf(fabsf(w)) * scale;
+                S.wv[rs][slot] = w;
+            }
+            if (pw == 0 && lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
             __syncwarp();
             if (lane == 0) {
-                S.meta_raw[rs] = (uint32_t)cnt | flags;
-                mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)cnt * D * 4);
+                if (nmine > 0) mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)nmine * D * 4);
+                else mbar_arrive(&S.raw_full[rs]);
             }
             __syncwarp();
-            if (mine) bulk_g2s(&S.raw[rs][slot * RAWP], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
+            if (mine) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
             if (++rs == NR) { rs = 0; rph ^= 1u; }
         };
         int row, slot_unused;
@@ -240,14 +273,13 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         // stop marker
         mbar_wait(&S.raw_empty[rs], rph ^ 1u);
         if (lane == 0) {
-            S.meta_raw[rs] = F_STOP;
+            if (pw == 0) S.meta_raw[rs] = F_STOP;
             mbar_arrive(&S.raw_full[rs]);
         }
     } else if (warp == W_MMA) {
         // ================= MMA issue =================
         uint32_t os = 0, oph = 0, acc = 0, aph = 0;
-        const uint32_t idesc = idesc_tf32_mn(128, 128), idesc_neg = idesc | (1u << 13);
-        const uint32_t idesc_w = idesc_tf32_mn(128, 256), idesc_w_neg = idesc_w | (1u << 13);   // d = 256: N = 256
+        const uint32_t idesc = idesc_f16_k(128, 128), idesc_w = idesc_f16_k(128, 256);   // d = 256: N = 256
         bool row_open = false;
         for (;;) {
             mbar_wait(&S.op_full[os], oph);
@@ -261,31 +293,30 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
             if (lane == 0) {
                 const int ksteps = (int)(meta & 0xffu);
-                const uint32_t id = (meta & F_NEG) ? idesc_neg : idesc;
+                const uint32_t neg = (meta & F_NEG) ? IDESC_NEGATE_A : 0u;
                 const uint32_t hi = s32(&S.op[os][0][0]), lo = s32(&S.op[os][1][0]);
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint32_t acc0 = (row_open || ks > 0) ? 1u : 0u;
-                    // MN-major tf32 operand: SWIZZLE_128B_BASE32B atoms of 32 (M/N) x 4 (K) values = 512 B; the next 4 k
-                    // 512 B further (stride-dimension offset), the next 32 columns 1024 B further (leading-dimension offset)
-                    const uint64_t dh = smem_desc(hi + ks * KSTEP_FLOATS * 4, 1024, 512) | SWZ_128B_BASE32B;
-                    const uint64_t dl = smem_desc(lo + ks * KSTEP_FLOATS * 4, 1024, 512) | SWZ_128B_BASE32B;
+                    // K = 16 = two 8-k chunks: LBO apart; neighbouring 8-feature core matrices 128 B apart (SBO)
+                    const uint64_t dh = smem_desc(hi + ks * 2 * LBO, LBO, 128);
+                    const uint64_t dl = smem_desc(lo + ks * 2 * LBO, LBO, 128);
                     if (D == 128) {
                         const uint32_t dcol = tmem + D * (1 + acc);
-                        mma_tf32(dcol, dh, dh, id, acc0);
-                        mma_tf32(dcol, dh, dl, id, 1u);
-                        mma_tf32(dcol, dl, dh, id, 1u);
+                        mma_f16(dcol, dh, dh, idesc | neg, acc0);
+                        mma_f16(dcol, dh, dl, idesc | neg, 1u);
+                        mma_f16(dcol, dl, dh, idesc | neg, 1u);
                     } else {
                         // rows 0..127 x columns 0..255 -> tensor-memory columns [0, 256)
-                        const uint32_t idw = (meta & F_NEG) ? idesc_w_neg : idesc_w;
-                        mma_tf32(tmem, dh, dh, idw, acc0);
-                        mma_tf32(tmem, dh, dl, idw, 1u);
-                        mma_tf32(tmem, dl, dh, idw, 1u);
-                        // rows 128..255 x columns 128..255 -> tensor-memory columns [256, 384): the slab's second half
-                        const uint64_t eh = smem_desc(hi + ks * KSTEP_FLOATS * 4 + 4096, 1024, 512) | SWZ_128B_BASE32B;
-                        const uint64_t el = smem_desc(lo + ks * KSTEP_FLOATS * 4 + 4096, 1024, 512) | SWZ_128B_BASE32B;
-                        mma_tf32(tmem + 256, eh, eh, id, acc0);
-                        mma_tf32(tmem + 256, eh, el, id, 1u);
-                        mma_tf32(tmem + 256, el, eh, id, 1u);
+                        mma_f16(tmem, dh, dh, idesc_w | neg, acc0);
+                        mma_f16(tmem, dh, dl, idesc_w | neg, 1u);
+                        mma_f16(tmem, dl, dh, idesc_w | neg, 1u);
+                        // rows 128..255 x columns 128..255 -> tensor-memory columns [256, 384): features 128.. start 16
+                        // core matrices (2048 B) into the slab
+                        const uint64_t eh = smem_desc(hi + ks * 2 * LBO + 2048, LBO, 128);
+                        const uint64_t el = smem_desc(lo + ks * 2 * LBO + 2048, LBO, 128);
+                        mma_f16(tmem + 256, eh, eh, idesc | neg, acc0);
+                        mma_f16(tmem + 256, eh, el, idesc | neg, 1u);
+                        mma_f16(tmem + 256, el, eh, idesc | neg, 1u);
                     }
                 }
                 mma_commit(&S.op_empty[os]);
@@ -299,24 +330,15 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             if (++os == NO) { os = 0; oph ^= 1u; }
         }
     } else if (warp >= W_CONV && warp < W_CONV + N_CONV) {
-        // ================= convert: raw fp32 -> scaled tf32 head/tail operand slabs =================
-        // thread -> gathered row k = 4*kg + k4 of the tile and the 16-byte column chunks j = jpar + 2*(jsel + JS*i).
-        // lane bits 0-1 = k % 4 and bit 2 = chunk parity make every quarter-warp hit 8 distinct 16-byte bank groups,
-        // both on the raw read (pitch D+8 floats) and on the swizzled operand write.
+        // ================= convert: raw fp32 -> scaled fp16 head/tail operand slabs =================
+        // thread ct owns features m = ct + 128 f: a warp reads 32 consecutive floats of one gathered row (conflict-free)
+        // and writes 32 consecutive 16-byte groups of a core-matrix column (conflict-free).
         const int ct = tid - W_CONV * 32;
-        constexpr int KG = Cfg<D>::KG, JS = Cfg<D>::JS, NPART = Cfg<D>::NPART;
-        const int k4 = ct & 3, jpar = (ct >> 2) & 1, rest = ct >> 3;
-        const int kg = rest % KG, jsel = rest / KG;
-        const int k = 4 * kg + k4;
-        const int part = NPART == 2 ? ((ct >> 5) & 1) : 0;          // which half of the k groups this warp covers
-        // element (k, column m = 4j..4j+3) of a K = 8 slab, in floats:
-        //   (m/32)*256 + ((k%8)/4)*128 + (k%4)*32 + ((((m%32)/8) ^ (k%4))*8) + m%8
-        const int op_base = (k >> 3) * KSTEP_FLOATS + ((k >> 2) & 1) * 128 + k4 * 32 + jpar * 4;
         uint32_t rs = 0, rph = 0, os = 0, oph = 0, bslot = 0;
-        float bacc[32], qacc[32];
+        float2 bacc[NF], qacc[NF];
         float wacc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { bacc[i] = 0.f; qacc[i] = 0.f; }
+        for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
         for (;;) {
             mbar_wait(&S.raw_full[rs], rph);
             const uint32_t meta = S.meta_raw[rs];
@@ -326,59 +348,79 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 mbar_arrive(&S.op_full[os]);
                 break;
             }
-            const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 7) >> 3;
+            const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 15) >> 4;
             if (meta & F_FIRST) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { bacc[i] = 0.f; qacc[i] = 0.f; }
+                for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
                 wacc = 0.f;
             }
-            if (k < ksteps * 8) {
-                const bool valid = k < cnt;
-                const float swv = valid ? S.sw[rs][k] : 0.f;
-                const float sa = fabsf(swv);
-                if (jpar == 0 && jsel == 0) wacc = fmaf(swv, sa, wacc);
-                float* hi = &S.op[os][0][op_base];
-                float* lo = &S.op[os][1][op_base];
-                const float* rp = &S.raw[rs][k * RAWP];
+            const float* rawp = &S.raw[rs][0];
+            unsigned char* hi = &S.op[os][0][0];
+            unsigned char* lo = &S.op[os][1][0];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int j = jpar + 2 * (jsel + JS * i);   // 16-byte column chunk
-                    const int o = (j >> 3) * 256 + ((((j & 7) >> 1) ^ k4) * 8);
-                    float4 q = valid ? *reinterpret_cast<const float4*>(rp + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 s = make_float4(q.x * sa, q.y * sa, q.z * sa, q.w * sa), h, l;
-                    split_tf32(s.x, h.x, l.x);
-                    split_tf32(s.y, h.y, l.y);
-                    split_tf32(s.z, h.z, l.z);
-                    split_tf32(s.w, h.w, l.w);
-                    *reinterpret_cast<float4*>(hi + o) = h;
-                    *reinterpret_cast<float4*>(lo + o) = l;
-                    bacc[4 * i + 0] = fmaf(swv, s.x, bacc[4 * i + 0]);
-                    bacc[4 * i + 1] = fmaf(swv, s.y, bacc[4 * i + 1]);
-                    bacc[4 * i + 2] = fmaf(swv, s.z, bacc[4 * i + 2]);
-                    bacc[4 * i + 3] = fmaf(swv, s.w, bacc[4 * i + 3]);
-                    if (ta.loss_axis1) {
-                        qacc[4 * i + 0] += q.x; qacc[4 * i + 1] += q.y; qacc[4 * i + 2] += q.z; qacc[4 * i + 3] += q.w;
+            for (int kc = 0; kc < TILE / 8; ++kc) {
+                if (kc < 2 * ksteps) {
+                    const int k0 = kc * 8;
+                    float4 sa = *reinterpret_cast<const float4*>(&S.sws[rs][k0]);
+                    float4 sb = *reinterpret_cast<const float4*>(&S.sws[rs][k0 + 4]);
+                    float4 wa = *reinterpret_cast<const float4*>(&S.wv[rs][k0]);
+                    float4 wb = *reinterpret_cast<const float4*>(&S.wv[rs][k0 + 4]);
+                    const bool full = k0 + 8 <= cnt;      // warp-uniform
+                    if (!full) {   // the stage's slots >= cnt hold stale data: weight and scale 0, value 0
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (k0 >= cnt) { sa = z; sb = z; wa = z; wb = z; }
+                        else {
+                            const int r = cnt - k0;   // 1..7 valid
+                            if (r < 2) { sa.y = 0.f; wa.y = 0.f; }
+                            if (r < 3) { sa.z = 0.f; wa.z = 0.f; }
+                            if (r < 4) { sa.w = 0.f; wa.w = 0.f; }
+                            if (r < 5) { sb.x = 0.f; wb.x = 0.f; }
+                            if (r < 6) { sb.y = 0.f; wb.y = 0.f; }
+                            if (r < 7) { sb.z = 0.f; wb.z = 0.f; }
+                            sb.w = 0.f; wb.w = 0.f;
+                        }
+                    }
+                    if (ta.loss_axis1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        const int m = ct + 128 * f;
+                        float q[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
+                        if (!full) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
+                        }
+                        const float2 q01 = make_float2(q[0], q[1]), q23 = make_float2(q[2], q[3]);
+                        const float2 q45 = make_float2(q[4], q[5]), q67 = make_float2(q[6], q[7]);
+                        uint4 h4, l4;
+                        split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
+                        split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
+                        split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
+                        split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
+                        const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
+                        *reinterpret_cast<uint4*>(hi + off) = h4;
+                        *reinterpret_cast<uint4*>(lo + off) = l4;
+                        bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
+                        if (ta.loss_axis1) {
+                            qacc[f].x += (q[0] + q[2]) + (q[4] + q[6]);
+                            qacc[f].y += (q[1] + q[3]) + (q[5] + q[7]);
+                        }
                     }
                 }
             }
             fence_proxy_async_smem();
             mbar_arrive(&S.raw_empty[rs]);
             if (meta & F_LAST) {
-                // value index 4*i + comp <-> column 4*j(i) + comp; the 16 lanes sharing (jpar, jsel) are reduced
-                transpose_reduce16(bacc, lane);
-                if (ta.loss_axis1) transpose_reduce16(qacc, lane);
-                const int vi0 = ((lane >> 4) & 1) << 4 | ((lane >> 3) & 1) << 3 | ((lane >> 1) & 1) << 2 | (lane & 1) << 1;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int vi = vi0 + e;
-                    const int col = 4 * (jpar + 2 * (jsel + JS * (vi >> 2))) + (vi & 3);
-                    S.bvec[bslot][part][col] = bacc[e];
-                    if (ta.loss_axis1) S.sumq[bslot][part][col] = qacc[e];
+                for (int f = 0; f < NF; ++f) {
+                    S.bvec[bslot][ct + 128 * f] = bacc[f].x + bacc[f].y;
+                    if (ta.loss_axis1) S.sumq[bslot][ct + 128 * f] = qacc[f].x + qacc[f].y;
                 }
-                if (ta.loss_axis1 && jsel == 0) {   // warps whose threads (jpar == 0) see each gathered row once
-                    const float ws = warp_sum(jpar == 0 ? wacc : 0.f);
-                    if (lane == 0) S.wsum[bslot][part] = ws;
-                }
+                if (ta.loss_axis1 && ct == 0) S.wsum[bslot] = wacc;
                 bslot = (bslot + 1) & (NBV - 1);
             }
             if (ct == 0) S.meta_op[os] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
@@ -398,14 +440,19 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         const float tol = a.tol;
         int row = 0, slot = 0, nrow = 0, nslot = 0;
         int64_t beg, n = 0, nbeg, nn = 0;
-        int64_t seq = g;
+        // Three accumulators: the groups alternate rows (a group's previous use of a barrier is at least two rows back, so
+        // its phase parity is never stale).  One accumulator (d = 256): alternating groups would see only every other
+        // phase of the single barrier -- a parity wait two phases ahead passes falsely -- so both groups take every item
+        // and split its columns.
+        constexpr int SEQ_STEP = NACC == 1 ? 1 : 2;
+        int64_t seq = NACC == 1 ? 0 : g;
         float xj = 0.f, nxj = 0.f;
         if (my_first + seq * stride < nitems) {
             item_info(my_first + seq * stride, row, beg, n, slot);
             if (!PARTIAL) xj = a.X[(int64_t)row * a.ld + j];
         }
-        for (; my_first + seq * stride < nitems; seq += 2) {
-            const int64_t nit = my_first + (seq + 2) * stride;
+        for (; my_first + seq * stride < nitems; seq += SEQ_STEP) {
+            const int64_t nit = my_first + (seq + SEQ_STEP) * stride;
             if (nit < nitems) {
                 item_info(nit, nrow, nbeg, nn, nslot);
                 if (!PARTIAL) nxj = a.X[(int64_t)nrow * a.ld + j];
@@ -426,43 +473,36 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         tmem_ld32(dbase + c * 32, v);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) atomicAdd(sc + (size_t)j * D + c * 32 + i, v[i]);
+                        for (int i = 0; i < 32; ++i) atomicAdd(sc + (size_t)j * D + c * 32 + i, v[i] * inv2);
                     }
                 } else {
                     // tensor-memory columns [0,256): matrix rows 0..127; [256,384): rows 128..255 x columns 128..255;
                     // rows 128..255 x columns 0..127 are the transpose of rows 0..127 x columns 128..255
 #pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
+                    for (int c = 4 * g; c < 4 * g + 4; ++c) {
                         float v[32];
                         tmem_ld32(tmem + lane_off + c * 32, v);
                         tmem_wait_ld();
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            atomicAdd(sc + (size_t)j * D + c * 32 + i, v[i]);
-                            if (c >= 4) atomicAdd(sc + (size_t)(c * 32 + i) * D + j, v[i]);
+                            atomicAdd(sc + (size_t)j * D + c * 32 + i, v[i] * inv2);
+                            if (c >= 4) atomicAdd(sc + (size_t)(c * 32 + i) * D + j, v[i] * inv2);
                         }
                     }
 #pragma unroll 1
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 2 * g; c < 2 * g + 2; ++c) {
                         float v[32];
                         tmem_ld32(tmem + lane_off + 256 + c * 32, v);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) atomicAdd(sc + (size_t)(128 + j) * D + 128 + c * 32 + i, v[i]);
+                        for (int i = 0; i < 32; ++i) atomicAdd(sc + (size_t)(128 + j) * D + 128 + c * 32 + i, v[i] * inv2);
                     }
                 }
-                for (int jj = j; jj < D; jj += 128) {
-                    float bb = 0.f, qq = 0.f;
-#pragma unroll
-                    for (int pp = 0; pp < Cfg<D>::NPART; ++pp) {
-                        bb += S.bvec[bs][pp][jj];
-                        if (ta.loss_axis1) qq += S.sumq[bs][pp][jj];
-                    }
-                    atomicAdd(sc + (size_t)D * D + jj, bb);
-                    if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, qq);
+                for (int jj = j; jj < D && (NACC > 1 || g == 0); jj += 128) {
+                    atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][jj]);
+                    if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
                 }
-                if (ta.loss_axis1 && j == 0)
-                    atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs][0] + (Cfg<D>::NPART == 2 ? S.wsum[bs][1] : 0.f));
+                if (ta.loss_axis1 && j == 0 && (NACC > 1 || g == 0)) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
                 tc_fence_before();
                 mbar_arrive(&S.acc_empty[acc]);
                 row = nrow; slot = nslot; n = nn;
@@ -470,10 +510,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
             const uint32_t dbase = tmem + lane_off + 128 * (1 + acc);
             xs[j] = xj;
-            float bj = S.bvec[bs][0][j];
-            if (Cfg<D>::NPART == 2) bj += S.bvec[bs][Cfg<D>::NPART - 1][j];
+            const float bj = S.bvec[bs][j];
             group_sync(g);
-            // ---- h = (G + reg I) x + D x - b; keep the diagonal block of M in registers ----
+            // ---- h = (G + reg I) x + 2^-2e A x - b  (A = the accumulator); keep the diagonal block of M in registers ----
             float hG = 0.f, hD = 0.f;
             float md[32];
 #pragma unroll
@@ -495,9 +534,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 hG += g0 + g1;
                 if (c == q) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) md[i] = dv[i] + gv[i];
+                    for (int i = 0; i < 32; ++i) md[i] = fmaf(dv[i], inv2, gv[i]);
                 }
             }
+            hD *= inv2;
             if (a.compute_loss) {
                 // als.cc:298-321 with the pre-update row: reg*kappa*|x|^2 (both axes); item side additionally
                 // x G x + sum_obs[(1+w)(yhat-1)^2 - yhat^2] = x G x + x D x - 2 x.(b + sum q) + (n + sum w)
@@ -505,10 +545,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 double t = (double)(kappa * a.reg * xj * xj);
                 if (a.axis == 1) {
                     t += (double)xj * (double)(hG - a.reg * xj) + (double)xj * (double)hD -
-                         2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][0][j] +
-                                             (Cfg<D>::NPART == 2 ? (double)S.sumq[bs][Cfg<D>::NPART - 1][j] : 0.0));
+                         2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][j]);
                     if (j == 0) {
-                        const double ws = (double)S.wsum[bs][0] + (Cfg<D>::NPART == 2 ? (double)S.wsum[bs][1] : 0.0);
+                        const double ws = (double)S.wsum[bs];
                         t += (double)n + ws;
                         l_deno += (double)a.Y_rows + ws;
                     }
@@ -558,8 +597,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 d4 = *reinterpret_cast<const float4*>(&S.dl[g][B & 1][i]);
-                        u0 = fmaf(dv[i] + gv[i], d4.x, u0); u1 = fmaf(dv[i + 1] + gv[i + 1], d4.y, u1);
-                        u0 = fmaf(dv[i + 2] + gv[i + 2], d4.z, u0); u1 = fmaf(dv[i + 3] + gv[i + 3], d4.w, u1);
+                        u0 = fmaf(fmaf(dv[i], inv2, gv[i]), d4.x, u0);
+                        u1 = fmaf(fmaf(dv[i + 1], inv2, gv[i + 1]), d4.y, u1);
+                        u0 = fmaf(fmaf(dv[i + 2], inv2, gv[i + 2]), d4.z, u0);
+                        u1 = fmaf(fmaf(dv[i + 3], inv2, gv[i + 3]), d4.w, u1);
                     }
                     h -= u0 + u1;
                 }
@@ -601,6 +642,22 @@ inline bool tc_split_applicable(int optimizer_code, int d, int vdim, int block_s
     return optimizer_code == 8 && (d == 128 || d == 256) && vdim == d && block_size == 32;
 }
 
+// device-side operand scale of the next tensor-core launches: maxes[0] = bits of max|Y| (noted at Gram time),
+// maxes[1] = bits of max|v| over the values of this launch
+inline int tc_note_absmax(const float* p, size_t n, unsigned int* out, int num_sms, cudaStream_t st) {
+    BFL_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned int), st));
+    if (n == 0) return BFL_OK;
+    const int grid = (int)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)num_sms * 8);
+    tc_absmax_kernel<<<grid, 256, 0, st>>>(p, n, out);
+    BFL_LAUNCHED();
+    return BFL_OK;
+}
+inline int tc_update_scale(const unsigned int* ymax, const unsigned int* vmax, float alpha, float* scales, cudaStream_t st) {
+    tc_scale_kernel<<<1, 1, 0, st>>>(ymax, vmax, alpha, scales);
+    BFL_LAUNCHED();
+    return BFL_OK;
+}
+
 // split-row items: every row of list[0..nrows) is cut into chunks of `split` entries -> triples (row, chunk, slot)
 __global__ void tc_count_items_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ list, int64_t nrows,
                                       int64_t split, unsigned long long* total) {
@@ -630,6 +687,7 @@ template <int D>
 int tc_launch_partial(const AlsArgs& a, const int32_t* items, int64_t nitems, float* scratch, int64_t nslots,
                       int64_t split, int num_sms, cudaStream_t st) {
     if (nitems <= 0) return BFL_OK;
+    if (!a.tc_scales) BFL_FAIL(BFL_ERR_STATE, "tensor-core ALS kernel: operand scale not prepared");
     TcArgs ta;
     ta.a = a;
     ta.a.row_begin = 0;
@@ -651,6 +709,7 @@ int tc_launch_partial(const AlsArgs& a, const int32_t* items, int64_t nitems, fl
 inline int tc_launch(const AlsArgs& a, int num_sms, cudaStream_t st) {
     const int64_t nrows = a.row_end - a.row_begin;
     if (nrows <= 0) return BFL_OK;
+    if (!a.tc_scales) BFL_FAIL(BFL_ERR_STATE, "tensor-core ALS kernel: operand scale not prepared");
     TcArgs ta;
     ta.a = a;
     ta.items = nullptr;

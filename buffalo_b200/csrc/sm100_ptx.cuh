@@ -1,6 +1,6 @@
 // Thin inline-PTX wrappers for the sm_100a features the tensor-core ALS kernel uses: mbarrier, 1-D bulk async
-// copies (TMA, SASS UBLKCP), tensor memory (tcgen05.alloc/ld, SASS LDTM) and tcgen05.mma kind::tf32 (SASS UTCHMMA)
-// with shared-memory matrix descriptors.  No CUTLASS: every string below is plain PTX ISA 8.8.
+// copies (TMA, SASS UBLKCP), tensor memory (tcgen05.alloc/ld, SASS LDTM) and tcgen05.mma kind::f16 / kind::tf32
+// (SASS UTCHMMA) with shared-memory matrix descriptors.  No CUTLASS: every string below is plain PTX ISA 8.8.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -102,31 +102,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         : "memory");
 }
 
-// ---- tcgen05.mma kind::tf32, operands from shared memory, fp32 accumulator in tensor memory ------------
+// ---- tcgen05.mma, operands from shared memory, fp32 accumulator in tensor memory ------------------------
 // Shared-memory matrix descriptor (PTX ISA "matrix descriptor", tcgen05 flavour: bits 46-47 = 0b01):
 //   [0,14) start address >> 4 | [16,30) leading-dimension byte offset >> 4 | [32,46) stride-dimension byte offset >> 4
 //   [61,64) swizzle mode (0 = none)
-// MN-major operand without swizzle: the unit is an 8 (K) x 16-byte (4 tf32 along M/N) core matrix stored as 8
-// consecutive 16-byte rows (128 B); SBO is the distance between core matrices that are neighbours along M/N, LBO
-// the distance between neighbours along K (unused at K = 8, one core matrix deep).
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
            ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-// instruction descriptor: D fp32, A/B tf32, both operands MN-major ("transposed"), M x N tile, dense, no negate
-__host__ __device__ constexpr uint32_t idesc_tf32_mn(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
-// one thread issues; D[tmem] (+)= A^T-tile . B-tile over K = 8
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
 }
 // arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -134,12 +116,46 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-// round-to-nearest split of an fp32 value into a tf32 head and an fp32 tail (head + tail == x exactly)
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    lo = x - hi;
+// ---- tcgen05.mma kind::f16 (fp16 operands, fp32 accumulator) -------------------------------------------
+// K-major un-swizzled ("interleaved") operand: core matrices of 8 rows (M/N) x 16 bytes (8 fp16 along K), stored as 128
+// contiguous bytes; SBO = distance between core matrices that are neighbours along M/N, LBO = distance between
+// neighbours along K (probe: benchmarks/mma_probe.cu).  One instruction covers K = 16 (two core matrices deep).
+__host__ __device__ constexpr uint32_t idesc_f16_k(int M, int N) {   // D fp32, A/B fp16, both K-major, dense
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+constexpr uint32_t IDESC_NEGATE_A = 1u << 13;
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// packed fp32 pairs (Blackwell FMUL2 / FFMA2)
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+// Two-term fp16 split of a pair of fp32 values (k even -> low half, k odd -> high half of each 32-bit word):
+// head = the value with its low 13 mantissa bits cleared (exactly an fp16 number while it is in the normal fp16 range),
+// tail = value - head rounded to fp16; head + tail carries >= 21 significant bits.
+__device__ __forceinline__ void split_f16x2(float2 s, uint32_t& head, uint32_t& tail) {
+    float2 h;
+    h.x = __uint_as_float(__float_as_uint(s.x) & 0xffffe000u);
+    h.y = __uint_as_float(__float_as_uint(s.y) & 0xffffe000u);
+    const float2 t = f2fma(h, make_float2(-1.f, -1.f), s);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(head) : "f"(h.y), "f"(h.x));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(tail) : "f"(t.y), "f"(t.x));
 }
 
 }  // namespace sm100
