@@ -238,37 +238,96 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             if (mine) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
             if (++rs == NR) { rs = 0; rph ^= 1u; }
         };
-        int row, slot_unused;
-        int64_t beg = 0, n = 0;
-        int nrow = 0;
-        int64_t nbeg = 0, nn = 0;
-        if (my_first < nitems) item_info(my_first, row, beg, n, slot_unused);
-        for (int64_t it = my_first; it < nitems; it += stride) {
-            if (it + stride < nitems) item_info(it + stride, nrow, nbeg, nn, slot_unused);   // look-ahead
-            // first chunk's entries
-            const bool inl = lane < TILE;
-            int64_t idx = lane;
-            int32_t key = (inl && idx < n) ? a.keys[beg - a.shift + idx] : 0;
-            float w = (inl && idx < n) ? a.vals[beg - a.shift + idx] * a.alpha : 0.f;
-            for (int64_t c0 = 0; c0 < n; c0 += TILE) {
-                // prefetch the next chunk of this row
-                const int64_t idx2 = c0 + TILE + lane;
-                const int32_t key2 = (inl && idx2 < n) ? a.keys[beg - a.shift + idx2] : 0;
-                const float w2 = (inl && idx2 < n) ? a.vals[beg - a.shift + idx2] * a.alpha : 0.f;
-                const bool valid = inl && c0 + lane < n;
-                const unsigned pm = __ballot_sync(FULL, valid && !(w < 0.f));
-                const unsigned nm = __ballot_sync(FULL, valid && (w < 0.f));
-                const bool lastc = c0 + TILE >= n;
-                uint32_t fl = (c0 == 0 ? F_FIRST : 0u);
-                if (pm) {
-                    emit(pm, fl | ((lastc && !nm) ? F_LAST : 0u), key, w);
-                    fl = 0u;
+        // Software pipeline over the CTA's items.  Every level of the dependent load chain  item -> row offsets -> entries
+        // is issued whole rows ahead of its use (a gathered tile takes ~700 cycles to issue, a global load ~1-2 thousand
+        // cycles under load: with a one-tile look-ahead every tile paid that latency):
+        //   item i+4: row id            item i+3: offsets            item i+2: first super-chunk of entries (keys, weights)
+        // and inside a long row the next super-chunk (SC tiles) is loaded while the current one is being emitted.
+        constexpr int SC = 4, SCN = SC * TILE;
+        const bool inl = lane < TILE;
+        auto load_id = [&](int64_t it, int& row, int& chunk) {
+            row = -1;
+            chunk = 0;
+            if (it < nitems) {
+                if (PARTIAL) {
+                    const int32_t* p = ta.items + 3 * (a.row_begin + it);
+                    row = p[0];
+                    chunk = p[1];
+                } else {
+                    row = a.row_list[a.row_begin + it];
                 }
-                if (nm) emit(nm, fl | F_NEG | (lastc ? F_LAST : 0u), key, w);
-                key = key2;
-                w = w2;
             }
-            row = nrow; beg = nbeg; n = nn;
+        };
+        auto load_span = [&](int row, int chunk, int64_t& beg, int64_t& n) {
+            beg = 0;
+            n = 0;
+            if (row >= 0) {
+                const int64_t rb = row == 0 ? 0 : a.indptr[row - 1];
+                const int64_t rn = a.indptr[row] - rb;
+                if (PARTIAL) {
+                    beg = rb + (int64_t)chunk * ta.split;
+                    n = min(ta.split, rn - (int64_t)chunk * ta.split);
+                } else {
+                    beg = rb;
+                    n = rn;
+                }
+            }
+        };
+        auto load_sc = [&](int64_t beg, int64_t n, int64_t c0, int32_t (&key)[SC], float (&w)[SC]) {
+#pragma unroll
+            for (int s = 0; s < SC; ++s) {
+                const int64_t idx = c0 + s * TILE + lane;
+                const bool ok = inl && idx < n;
+                key[s] = ok ? a.keys[beg - a.shift + idx] : 0;
+                w[s] = ok ? a.vals[beg - a.shift + idx] * a.alpha : 0.f;
+            }
+        };
+        int64_t beg0, n0, beg1, n1, beg2, n2, beg3, n3;
+        int row_t, ch_t, row4, ch4;
+        int32_t k0[SC], k1[SC], k2[SC], nk[SC];
+        float w0[SC], w1[SC], w2[SC], nw[SC];
+        load_id(my_first, row_t, ch_t);
+        load_span(row_t, ch_t, beg0, n0);
+        load_sc(beg0, n0, 0, k0, w0);
+        load_id(my_first + stride, row_t, ch_t);
+        load_span(row_t, ch_t, beg1, n1);
+        load_sc(beg1, n1, 0, k1, w1);
+        load_id(my_first + 2 * stride, row_t, ch_t);
+        load_span(row_t, ch_t, beg2, n2);
+        load_id(my_first + 3 * stride, row4, ch4);
+        for (int64_t it = my_first; it < nitems; it += stride) {
+            // issue the look-ahead loads (their results are first touched one item later)
+            load_sc(beg2, n2, 0, k2, w2);
+            load_span(row4, ch4, beg3, n3);
+            load_id(it + 4 * stride, row4, ch4);
+            for (int64_t c0 = 0; c0 < n0; c0 += SCN) {
+                const bool more = c0 + SCN < n0;
+                if (more) load_sc(beg0, n0, c0 + SCN, nk, nw);
+#pragma unroll
+                for (int s = 0; s < SC; ++s) {
+                    const int64_t t0 = c0 + s * TILE;
+                    if (t0 < n0) {
+                        const float w = w0[s];
+                        const bool valid = inl && t0 + lane < n0;
+                        const unsigned pm = __ballot_sync(FULL, valid && !(w < 0.f));
+                        const unsigned nm = __ballot_sync(FULL, valid && (w < 0.f));
+                        const bool lastc = t0 + TILE >= n0;
+                        uint32_t fl = (t0 == 0 ? F_FIRST : 0u);
+                        if (pm) {
+                            emit(pm, fl | ((lastc && !nm) ? F_LAST : 0u), k0[s], w);
+                            fl = 0u;
+                        }
+                        if (nm) emit(nm, fl | F_NEG | (lastc ? F_LAST : 0u), k0[s], w);
+                    }
+                }
+                if (more) {
+#pragma unroll
+                    for (int s = 0; s < SC; ++s) { k0[s] = nk[s]; w0[s] = nw[s]; }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SC; ++s) { k0[s] = k1[s]; w0[s] = w1[s]; k1[s] = k2[s]; w1[s] = w2[s]; }
+            beg0 = beg1; n0 = n1; beg1 = beg2; n1 = n2; beg2 = beg3; n2 = n3;
         }
         // stop marker
         mbar_wait(&S.raw_empty[rs], rph ^ 1u);
