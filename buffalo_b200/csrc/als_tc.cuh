@@ -17,22 +17,27 @@
 // 2^-2e (exact) when it is read.  b and the loss pieces are accumulated in plain fp32 from the unscaled rows.
 //
 // Pipeline of one persistent CTA (one per SM, 16 warps, warp-specialised, mbarrier hand-offs only):
-//   3 producer warps : walk the CTA's rows in lock step; per tile of 32 gathered opposite-factor rows every warp issues a
-//                     third of the 512-byte cp.async.bulk copies (TMA, SASS UBLKCP).  A divergent-address bulk copy
-//                     compiles to an ELECT / R2UR / UBLKCP loop over the lanes, ~63 cycles per copy and warp: one warp
+//   planner warp     : walks the CTA's rows; every level of the dependent load chain (row id -> offsets -> keys / values)
+//                     is issued whole rows ahead of its use; per tile of 32 entries it writes the gather plan (keys,
+//                     2^e sqrt|w|, w, count / flags) into the tile's ring slot;
+//   6 issuer warps   : turn a plan into 512-byte cp.async.bulk copies (TMA, SASS UBLKCP) of the gathered opposite-factor
+//                     rows into the ring of raw fp32 tiles, completion by mbarrier expect_tx.  A divergent-address bulk
+//                     copy compiles to an ELECT / R2UR / UBLKCP loop over the lanes, ~63 cycles per copy and warp: one warp
 //                     alone sustains 2.3 TB/s chip-wide, two 4.7, four or more the 7.0 TB/s HBM read ceiling
-//                     (benchmarks/gather_probe.cu); copies land in a ring of raw fp32 tiles, completion by mbarrier
-//                     expect_tx;
+//                     (benchmarks/gather_probe.cu) -- so the copies of a tile are dealt round-robin to six warps that do
+//                     nothing else;
 //   4 convert warps  : thread m owns feature m: reads column m of the raw tile (conflict-free), scales, splits, and writes
 //                     16-byte groups of 8 consecutive k into the K-major un-swizzled operand slabs (8 x 16 B core
 //                     matrices); accumulates b_m = sum w q_m (exact fp32) and the loss pieces in registers;
 //   MMA warp         : one lane issues tcgen05.mma kind::f16 (M = N = 128, K = 16; SASS UTCHMMA), accumulating the row's
 //                     matrix in tensor memory; entries with negative weight travel in their own tiles and are
 //                     subtracted with the instruction descriptor's negate-A bit;
-//   2 x 4 epilogue warps : thread j owns matrix row j (tensor-memory lane j): tcgen05.ld (SASS LDTM) the accumulator and
-//                     the resident G + reg*I (tensor memory columns 0..127), h = M x - b, then per 32-column block the
-//                     3-step CG in the owning warp and a rank-32 update of the later blocks' h.  Three accumulators
-//                     (3 x 128 columns) rotate, so the epilogue of rows i, i+1 overlaps the contraction of row i+2.
+//   4 epilogue warps : a systolic pipeline over rows.  Thread j owns matrix row j (tensor-memory lane j), warp q column
+//                     block q: tcgen05.ld (SASS LDTM) the accumulator and the resident G + reg*I (tensor memory columns
+//                     0..127), h = M x - b; then warp q folds the deltas of blocks 0..q-1 into its h as they are published,
+//                     runs the 3-step CG of its own 32 x 32 block and publishes its delta.  Nothing in a row's sweep is
+//                     a group-wide barrier, so warp 0 is already on the next row's block 0 while warp 3 finishes this
+//                     one: up to two of the three accumulators are being drained while the third is being filled.
 // Rows of any length stream through (no per-nnz state), which removes the long-row cliff of the SIMT classes; rows
 // longer than the split threshold are cut into chunks whose partial matrices are summed in global memory and solved
 // by als_explicit_solve_kernel (als_explicit.cuh).
@@ -48,9 +53,10 @@ using namespace sm100;
 
 // 16 warps x 128 registers fill the register file (registers are allocated for warp counts rounded up to 4: a 17th warp
 // would cap every thread at 96 registers and spill the epilogue)
-constexpr int N_PROD = 3, N_CONV = 4;
-constexpr int W_PROD = 0, W_MMA = 3, W_CONV = 4, W_EPI = 8;   // warps 8..11 epilogue group 0, 12..15 group 1
+constexpr int N_ISSUE = 6, N_CONV = 4;
+constexpr int W_PLAN = 0, W_MMA = 1, W_CONV = 4, W_EPI = 8;   // issuers: warps 2, 3, 12..15; epilogue warp 8 + q owns lane quarter q
 constexpr int WARPS = 16, THREADS = WARPS * 32;
+constexpr int NXS = 8;     // x buffers of the epilogue pipeline (a fast warp publishes row r + 1 while a slow one reads row r - 3)
 constexpr int NR = 6;      // raw stages
 constexpr int NO = 4;      // operand stages
 constexpr int NBV = 8;     // ring of per-row vectors handed from the convert warps to the epilogue
@@ -76,20 +82,20 @@ struct Smem {
     alignas(128) float raw[NR][TILE * D];              // gathered rows, pitch D
     alignas(16) float bvec[NBV][D];                    // b = sum w q
     alignas(16) float sumq[NBV][D];                    // sum q (loss only)
-    alignas(16) float xs[2][D];                        // 128-bit reads: every vector below is 16-byte aligned
-    alignas(16) float pv[2][32];
-    alignas(16) float dl[2][2][32];
-    alignas(16) float sws[NR][TILE];                   // 2^e sqrt|w| per slot
-    alignas(16) float wv[NR][TILE];                    // w per slot
+    alignas(16) float xs[NXS][D];                      // 128-bit reads: every vector below is 16-byte aligned
+    alignas(16) float pv[4][32];                       // CG direction of the warp that owns the block
+    alignas(16) float dl[NACC_MAX][4][32];             // [row slot][block]: the block's solution delta
+    alignas(16) float sws[NR][TILE];                   // gather plan: 2^e sqrt|w| per slot
+    alignas(16) float wv[NR][TILE];                    //              w per slot
+    alignas(16) int32_t keys[NR][TILE];                //              gathered row per slot
     float wsum[NBV];                                   // sum w (loss only)
     uint32_t meta_raw[NR];
     uint32_t meta_op[NO];
-    int badf[2][4];
-    alignas(8) uint64_t raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO], acc_full[NACC_MAX], acc_empty[NACC_MAX];
+    int badrow[NXS];
+    alignas(8) uint64_t plan_full[NR], raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO];
+    alignas(8) uint64_t acc_full[NACC_MAX], acc_empty[NACC_MAX], x_full[NXS], d_full[NACC_MAX][4];
     uint32_t tmem_base;
 };
-
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory"); }
 
 // PARTIAL = false: rows of a.row_list[row_begin..row_end) are solved in place.
 // PARTIAL = true : the list holds chunk items of long rows (pairs: row, chunk index); the chunk's matrix and vectors are
@@ -150,7 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 
     if (tid == 0) {
         for (int i = 0; i < NR; ++i) {
-            mbar_init(&S.raw_full[i], N_PROD);
+            mbar_init(&S.plan_full[i], 1);
+            mbar_init(&S.raw_full[i], N_ISSUE);
             mbar_init(&S.raw_empty[i], N_CONV * 32);
         }
         for (int i = 0; i < NO; ++i) {
@@ -159,7 +166,12 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&S.acc_full[i], 1);
-            mbar_init(&S.acc_empty[i], NACC == 1 ? 256 : 128);   // one accumulator: both epilogue groups drain it together
+            mbar_init(&S.acc_empty[i], 128);
+            for (int b = 0; b < 4; ++b) mbar_init(&S.d_full[i][b], 1);
+        }
+        for (int i = 0; i < NXS; ++i) {
+            mbar_init(&S.x_full[i], 128);
+            S.badrow[i] = 0;
         }
         mbar_init_fence();
     }
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
     const uint32_t tmem = S.tmem_base;
     const float scale = __ldg(a.tc_scales), inv2 = __ldg(a.tc_scales + 1);
 
-    // G + reg I -> tensor memory columns [0, D) (epilogue group 0; thread j holds matrix row j)
+    // G + reg I -> tensor memory columns [0, D) (thread j of the epilogue holds matrix row j)
     if (!PARTIAL && warp >= W_EPI && warp < W_EPI + 4) {
         const int q = warp & 3, j = q * 32 + lane;
 #pragma unroll 1
@@ -213,29 +225,21 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         }
     };
 
-    if (warp < W_PROD + N_PROD) {
-        // ================= producers: gathers =================
-        // All producer warps walk the same tile sequence; warp pw issues the copies of the slots with slot % N_PROD == pw.
-        const int pw = warp - W_PROD;
+    if (warp == W_PLAN) {
+        // ================= planner: gather plans =================
         uint32_t rs = 0, rph = 0;   // stage, phase of raw_empty
         auto emit = [&](unsigned mask, uint32_t flags, int32_t key, float w) {
             const int cnt = __popc(mask);
             const int slot = __popc(mask & ((1u << lane) - 1u));
-            const bool mine = ((mask >> lane) & 1u) && slot % N_PROD == pw;
-            const int nmine = (cnt + N_PROD - 1 - pw) / N_PROD;
             mbar_wait(&S.raw_empty[rs], rph ^ 1u);
-            if (mine) {
+            if ((mask >> lane) & 1u) {
+                S.keys[rs][slot] = key;
                 S.sws[rs][slot] = sqrtf(fabsf(w)) * scale;
                 S.wv[rs][slot] = w;
             }
-            if (pw == 0 && lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
+            if (lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
             __syncwarp();
-            if (lane == 0) {
-                if (nmine > 0) mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)nmine * D * 4);
-                else mbar_arrive(&S.raw_full[rs]);
-            }
-            __syncwarp();
-            if (mine) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
+            if (lane == 0) mbar_arrive(&S.plan_full[rs]);
             if (++rs == NR) { rs = 0; rph ^= 1u; }
         };
         // Software pipeline over the CTA's items.  Every level of the dependent load chain  item -> row offsets -> entries
@@ -332,8 +336,32 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         // stop marker
         mbar_wait(&S.raw_empty[rs], rph ^ 1u);
         if (lane == 0) {
-            if (pw == 0) S.meta_raw[rs] = F_STOP;
-            mbar_arrive(&S.raw_full[rs]);
+            S.meta_raw[rs] = F_STOP;
+            mbar_arrive(&S.plan_full[rs]);
+        }
+    } else if (warp == 2 || warp == 3 || warp >= W_EPI + 4) {
+        // ================= issuers: plan -> bulk copies =================
+        const int is = warp < 4 ? warp - 2 : warp - (W_EPI + 4) + 2;   // 0..5; issuer `is` copies the slots is, is + 6, ...
+        uint32_t rs = 0, ph = 0;
+        for (;;) {
+            mbar_wait(&S.plan_full[rs], ph);
+            const uint32_t meta = S.meta_raw[rs];
+            if (meta & F_STOP) {
+                if (lane == 0) mbar_arrive(&S.raw_full[rs]);
+                break;
+            }
+            const int cnt = (int)(meta & 0xffu);
+            const int slot = is + N_ISSUE * lane;
+            const bool mine = slot < cnt;
+            const int nmine = cnt > is ? (cnt - is + N_ISSUE - 1) / N_ISSUE : 0;
+            const int32_t key = mine ? S.keys[rs][slot] : 0;
+            if (lane == 0) {
+                if (nmine > 0) mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)nmine * D * 4);
+                else mbar_arrive(&S.raw_full[rs]);
+            }
+            __syncwarp();
+            if (mine) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
+            if (++rs == NR) { rs = 0; ph ^= 1u; }
         }
     } else if (warp == W_MMA) {
         // ================= MMA issue =================
@@ -488,41 +516,26 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             if (++os == NO) { os = 0; oph ^= 1u; }
         }
     } else {
-        // ================= epilogue: explicit-matrix block Gauss-Seidel / CG =================
-        const int g = (warp - W_EPI) >> 2;      // group
+        // ================= epilogue: explicit-matrix block Gauss-Seidel / CG, systolic over rows =================
         const int q = warp & 3;                  // tensor-memory lane quarter == column block owned by this warp
         const int j = q * 32 + lane;             // matrix row
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        float* xs = S.xs[g];
-        float* pv = S.pv[g];
+        float* pv = S.pv[q];
         double l_nume = 0.0, l_deno = 0.0;
         const float tol = a.tol;
-        int row = 0, slot = 0, nrow = 0, nslot = 0;
-        int64_t beg, n = 0, nbeg, nn = 0;
-        // Three accumulators: the groups alternate rows (a group's previous use of a barrier is at least two rows back, so
-        // its phase parity is never stale).  One accumulator (d = 256): alternating groups would see only every other
-        // phase of the single barrier -- a parity wait two phases ahead passes falsely -- so both groups take every item
-        // and split its columns.
-        constexpr int SEQ_STEP = NACC == 1 ? 1 : 2;
-        int64_t seq = NACC == 1 ? 0 : g;
-        float xj = 0.f, nxj = 0.f;
-        if (my_first + seq * stride < nitems) {
-            item_info(my_first + seq * stride, row, beg, n, slot);
-            if (!PARTIAL) xj = a.X[(int64_t)row * a.ld + j];
-        }
-        for (; my_first + seq * stride < nitems; seq += SEQ_STEP) {
-            const int64_t nit = my_first + (seq + SEQ_STEP) * stride;
-            if (nit < nitems) {
-                item_info(nit, nrow, nbeg, nn, nslot);
-                if (!PARTIAL) nxj = a.X[(int64_t)nrow * a.ld + j];
-            }
-            const uint32_t acc = (uint32_t)(seq % NACC), aph = (uint32_t)((seq / NACC) & 1);
-            const uint32_t bs = (uint32_t)(seq & (NBV - 1));
-            mbar_wait(&S.acc_full[acc], aph);
-            tc_fence_after();
-            if constexpr (PARTIAL) {
-                // add this chunk's matrix / vectors to the row's scratch block (float atomics: the chunks of one row
-                // are summed in arrival order)
+        if constexpr (PARTIAL) {
+            // add every chunk's matrix / vectors to the row's scratch block (float atomics: the chunks of one row are
+            // summed in arrival order); the four warps are independent here
+            int row = 0, slot = 0, nrow = 0, nslot = 0;
+            int64_t beg, n = 0, nbeg, nn = 0;
+            if (my_first < nitems) item_info(my_first, row, beg, n, slot);
+            for (int64_t seq = 0; my_first + seq * stride < nitems; ++seq) {
+                const int64_t nit = my_first + (seq + 1) * stride;
+                if (nit < nitems) item_info(nit, nrow, nbeg, nn, nslot);
+                const uint32_t acc = (uint32_t)(seq % NACC), aph = (uint32_t)((seq / NACC) & 1);
+                const uint32_t bs = (uint32_t)(seq & (NBV - 1));
+                mbar_wait(&S.acc_full[acc], aph);
+                tc_fence_after();
                 float* sc = ta.scratch + (size_t)slot * scratch_floats<D>();
                 if constexpr (D == 128) {
                     const uint32_t dbase = tmem + lane_off + D * (1 + acc);
@@ -538,7 +551,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     // tensor-memory columns [0,256): matrix rows 0..127; [256,384): rows 128..255 x columns 128..255;
                     // rows 128..255 x columns 0..127 are the transpose of rows 0..127 x columns 128..255
 #pragma unroll 1
-                    for (int c = 4 * g; c < 4 * g + 4; ++c) {
+                    for (int c = 0; c < 8; ++c) {
                         float v[32];
                         tmem_ld32(tmem + lane_off + c * 32, v);
                         tmem_wait_ld();
@@ -549,7 +562,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         }
                     }
 #pragma unroll 1
-                    for (int c = 2 * g; c < 2 * g + 2; ++c) {
+                    for (int c = 0; c < 4; ++c) {
                         float v[32];
                         tmem_ld32(tmem + lane_off + 256 + c * 32, v);
                         tmem_wait_ld();
@@ -557,68 +570,121 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         for (int i = 0; i < 32; ++i) atomicAdd(sc + (size_t)(128 + j) * D + 128 + c * 32 + i, v[i] * inv2);
                     }
                 }
-                for (int jj = j; jj < D && (NACC > 1 || g == 0); jj += 128) {
+                for (int jj = j; jj < D; jj += 128) {
                     atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][jj]);
                     if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
                 }
-                if (ta.loss_axis1 && j == 0 && (NACC > 1 || g == 0)) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
+                if (ta.loss_axis1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
                 tc_fence_before();
                 mbar_arrive(&S.acc_empty[acc]);
                 row = nrow; slot = nslot; n = nn;
-                continue;
             }
-            const uint32_t dbase = tmem + lane_off + 128 * (1 + acc);
-            xs[j] = xj;
-            const float bj = S.bvec[bs][j];
-            group_sync(g);
-            // ---- h = (G + reg I) x + 2^-2e A x - b  (A = the accumulator); keep the diagonal block of M in registers ----
-            float hG = 0.f, hD = 0.f;
-            float md[32];
-#pragma unroll
-            for (int c = 0; c < D / 32; ++c) {
-                float dv[32], gv[32];
-                tmem_ld32(dbase + c * 32, dv);
-                tmem_ld32(tmem + lane_off + c * 32, gv);
-                tmem_wait_ld();
-                float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(xs + c * 32 + i);
-                    h0 = fmaf(dv[i], x4.x, h0); h1 = fmaf(dv[i + 1], x4.y, h1);
-                    h0 = fmaf(dv[i + 2], x4.z, h0); h1 = fmaf(dv[i + 3], x4.w, h1);
-                    g0 = fmaf(gv[i], x4.x, g0); g1 = fmaf(gv[i + 1], x4.y, g1);
-                    g0 = fmaf(gv[i + 2], x4.z, g0); g1 = fmaf(gv[i + 3], x4.w, g1);
-                }
-                hD += h0 + h1;
-                hG += g0 + g1;
-                if (c == q) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) md[i] = fmaf(dv[i], inv2, gv[i]);
-                }
+        } else {
+            // Row pipeline registers: x_j of rows seq (xj), seq + 1 (x1), and the row ids of seq + 1, seq + 2; the loads
+            // for seq + 2 / seq + 3 are issued one iteration before they are touched.
+            auto row_of = [&](int64_t sq) -> int {
+                const int64_t it = my_first + sq * stride;
+                return it < nitems ? a.row_list[a.row_begin + it] : -1;
+            };
+            auto len_of = [&](int row) -> float {   // only for the adaptive-reg loss term
+                if (row < 0 || !a.compute_loss) return 0.f;
+                return (float)(a.indptr[row] - (row == 0 ? 0 : a.indptr[row - 1]));
+            };
+            int row = row_of(0), row1 = row_of(1), row2 = row_of(2);
+            float xj = row >= 0 ? a.X[(int64_t)row * a.ld + j] : 0.f;
+            float x1 = row1 >= 0 ? a.X[(int64_t)row1 * a.ld + j] : 0.f;
+            float nlen = len_of(row), nlen1 = len_of(row1);
+            if (row >= 0) {   // publish row 0's x
+                S.xs[0][j] = xj;
+                mbar_arrive(&S.x_full[0]);
             }
-            hD *= inv2;
-            if (a.compute_loss) {
-                // als.cc:298-321 with the pre-update row: reg*kappa*|x|^2 (both axes); item side additionally
-                // x G x + sum_obs[(1+w)(yhat-1)^2 - yhat^2] = x G x + x D x - 2 x.(b + sum q) + (n + sum w)
-                const float kappa = a.adaptive_reg ? (float)n : 1.0f;
-                double t = (double)(kappa * a.reg * xj * xj);
-                if (a.axis == 1) {
-                    t += (double)xj * (double)(hG - a.reg * xj) + (double)xj * (double)hD -
-                         2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][j]);
-                    if (j == 0) {
-                        const double ws = (double)S.wsum[bs];
-                        t += (double)n + ws;
-                        l_deno += (double)a.Y_rows + ws;
+            for (int64_t seq = 0; row >= 0; ++seq) {
+                // look-ahead loads
+                const int row3 = row_of(seq + 3);
+                const float x2 = row2 >= 0 ? a.X[(int64_t)row2 * a.ld + j] : 0.f;
+                const float nlen2 = len_of(row2);
+                if (row1 >= 0) {   // publish the next row's x: by the time a warp gets there everybody has
+                    S.xs[(seq + 1) & (NXS - 1)][j] = x1;
+                    mbar_arrive(&S.x_full[(seq + 1) & (NXS - 1)]);
+                }
+                const uint32_t acc = (uint32_t)(seq % NACC), aph = (uint32_t)((seq / NACC) & 1);
+                const uint32_t bs = (uint32_t)(seq & (NBV - 1));
+                const uint32_t xsl = (uint32_t)(seq & (NXS - 1));
+                const float* xs = S.xs[xsl];
+                mbar_wait(&S.x_full[xsl], (uint32_t)((seq / NXS) & 1));
+                mbar_wait(&S.acc_full[acc], aph);
+                tc_fence_after();
+                const uint32_t dbase = tmem + lane_off + 128 * (1 + acc);
+                const float bj = S.bvec[bs][j];
+                // ---- h = (G + reg I) x + 2^-2e A x - b  (A = the accumulator); keep the diagonal block of M in registers ----
+                float hG = 0.f, hD = 0.f;
+                float md[32];
+#pragma unroll
+                for (int c = 0; c < D / 32; ++c) {
+                    float dv[32], gv[32];
+                    tmem_ld32(dbase + c * 32, dv);
+                    tmem_ld32(tmem + lane_off + c * 32, gv);
+                    tmem_wait_ld();
+                    float h0 = 0.f, h1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 x4 = *reinterpret_cast<const float4*>(xs + c * 32 + i);
+                        h0 = fmaf(dv[i], x4.x, h0); h1 = fmaf(dv[i + 1], x4.y, h1);
+                        h0 = fmaf(dv[i + 2], x4.z, h0); h1 = fmaf(dv[i + 3], x4.w, h1);
+                        g0 = fmaf(gv[i], x4.x, g0); g1 = fmaf(gv[i + 1], x4.y, g1);
+                        g0 = fmaf(gv[i + 2], x4.z, g0); g1 = fmaf(gv[i + 3], x4.w, g1);
+                    }
+                    hD += h0 + h1;
+                    hG += g0 + g1;
+                    if (c == q) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) md[i] = fmaf(dv[i], inv2, gv[i]);
                     }
                 }
-                l_nume += t;
-            }
-            float h = hG + hD - bj;
-            // ---- block sweep ----
+                hD *= inv2;
+                if (a.compute_loss) {
+                    // als.cc:298-321 with the pre-update row: reg*kappa*|x|^2 (both axes); item side additionally
+                    // x G x + sum_obs[(1+w)(yhat-1)^2 - yhat^2] = x G x + x D x - 2 x.(b + sum q) + (n + sum w)
+                    const float kappa = a.adaptive_reg ? nlen : 1.0f;
+                    double t = (double)(kappa * a.reg * xj * xj);
+                    if (a.axis == 1) {
+                        t += (double)xj * (double)(hG - a.reg * xj) + (double)xj * (double)hD -
+                             2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][j]);
+                        if (j == 0) {
+                            const double ws = (double)S.wsum[bs];
+                            t += (double)nlen + ws;
+                            l_deno += (double)a.Y_rows + ws;
+                        }
+                    }
+                    l_nume += t;
+                }
+                float h = hG + hD - bj;
+                // ---- fold in the deltas of the earlier blocks as they appear: h -= M[j, B] . delta_B ----
 #pragma unroll 1
-            for (int B = 0; B < D / 32; ++B) {
-                if (q == B) {
-                    float r = h, p = h, xv = 0.f;
+                for (int B = 0; B < q; ++B) {
+                    float dv[32], gv[32];
+                    tmem_ld32(dbase + B * 32, dv);
+                    tmem_ld32(tmem + lane_off + B * 32, gv);
+                    mbar_wait(&S.d_full[acc][B], aph);
+                    tmem_wait_ld();
+                    float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 d4 = *reinterpret_cast<const float4*>(&S.dl[acc][B][i]);
+                        u0 = fmaf(fmaf(dv[i], inv2, gv[i]), d4.x, u0);
+                        u1 = fmaf(fmaf(dv[i + 1], inv2, gv[i + 1]), d4.y, u1);
+                        u0 = fmaf(fmaf(dv[i + 2], inv2, gv[i + 2]), d4.z, u0);
+                        u1 = fmaf(fmaf(dv[i + 3], inv2, gv[i + 3]), d4.w, u1);
+                    }
+                    h -= u0 + u1;
+                }
+                // this warp's reads of the accumulator are done
+                tc_fence_before();
+                mbar_arrive(&S.acc_empty[acc]);
+                // ---- 3-step CG on the own diagonal block (als.cc:324-345) ----
+                float xv = 0.f;
+                {
+                    float r = h, p = h;
                     float rsold = warp_sum(r * r);
                     bool act = rsold > tol;            // als.cc:329
 #pragma unroll 1
@@ -643,47 +709,44 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         if (act) p = fmaf(__fdividef(rsnew, rsold), p, r);
                         rsold = act ? rsnew : rsold;
                     }
-                    S.dl[g][B & 1][lane] = xv;
-                    xs[j] -= xv;                        // als.cc:346
                 }
-                group_sync(g);
-                if (q > B) {   // later blocks: h -= M[j, B] . delta
-                    float dv[32], gv[32];
-                    tmem_ld32(dbase + B * 32, dv);
-                    tmem_ld32(tmem + lane_off + B * 32, gv);
-                    tmem_wait_ld();
-                    float u0 = 0.f, u1 = 0.f;
+                float v = xj - xv;                      // als.cc:346
+                const bool badw = __any_sync(FULL, !isfinite(v));
+                // write the own block (and the peers' replicas, fused exchange) BEFORE publishing the delta: the warp of the
+                // last block may overwrite the row (NaN/Inf guard, cf. als.cu:116-120) and must come after these stores
+                a.X[(int64_t)row * a.ld + j] = v;
+                for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][(int64_t)row * a.ld + j] = v;
+                if (q < 3) {
+                    S.dl[acc][q][lane] = xv;
+                    if (badw && lane == 0) atomicOr(&S.badrow[xsl], 1);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.d_full[acc][q]);
+                }
+                // the warp of the last block has seen every earlier block's flag (set before that block's delta was
+                // published) and zeroes the whole row if any block came out non-finite
+                if (q == 3) {
+                    const bool bad = badw || (S.badrow[xsl] != 0);
+                    if (bad) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 d4 = *reinterpret_cast<const float4*>(&S.dl[g][B & 1][i]);
-                        u0 = fmaf(fmaf(dv[i], inv2, gv[i]), d4.x, u0);
-                        u1 = fmaf(fmaf(dv[i + 1], inv2, gv[i + 1]), d4.y, u1);
-                        u0 = fmaf(fmaf(dv[i + 2], inv2, gv[i + 2]), d4.z, u0);
-                        u1 = fmaf(fmaf(dv[i + 3], inv2, gv[i + 3]), d4.w, u1);
+                        for (int c = 0; c < 4; ++c) {
+                            a.X[(int64_t)row * a.ld + c * 32 + lane] = 0.f;
+                            for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][(int64_t)row * a.ld + c * 32 + lane] = 0.f;
+                        }
+                        __syncwarp();
+                        if (lane == 0) S.badrow[xsl] = 0;
                     }
-                    h -= u0 + u1;
                 }
+                row = row1; row1 = row2; row2 = row3;
+                xj = x1; x1 = x2;
+                nlen = nlen1; nlen1 = nlen2;
             }
-            // the accumulator is free again
-            tc_fence_before();
-            mbar_arrive(&S.acc_empty[acc]);
-            // NaN/Inf guard (cf. als.cu:116-120), write the row (and the peers' replicas, fused exchange)
-            float v = xs[j];
-            const bool badw = __any_sync(FULL, !isfinite(v));
-            if (lane == 0) S.badf[g][q] = badw;
-            group_sync(g);
-            const bool bad = S.badf[g][0] | S.badf[g][1] | S.badf[g][2] | S.badf[g][3];
-            v = bad ? 0.f : v;
-            a.X[(int64_t)row * a.ld + j] = v;
-            for (int pr = 0; pr < a.n_peer; ++pr) a.peerX[pr][(int64_t)row * a.ld + j] = v;
-            row = nrow; slot = nslot; n = nn; xj = nxj;
-        }
-        if (!PARTIAL && a.loss && a.compute_loss) {
-            l_nume = warp_sum_d(l_nume);
-            l_deno = warp_sum_d(l_deno);
-            if (lane == 0 && (l_nume != 0.0 || l_deno != 0.0)) {
-                atomicAdd(a.loss, l_nume);
-                atomicAdd(a.loss + 1, l_deno);
+            if (a.loss && a.compute_loss) {
+                l_nume = warp_sum_d(l_nume);
+                l_deno = warp_sum_d(l_deno);
+                if (lane == 0 && (l_nume != 0.0 || l_deno != 0.0)) {
+                    atomicAdd(a.loss, l_nume);
+                    atomicAdd(a.loss + 1, l_deno);
+                }
             }
         }
     }
