@@ -44,6 +44,8 @@
 #pragma once
 #include "als_generic.cuh"
 #include "bfl_common.cuh"
+#include <type_traits>
+
 #include "sm100_ptx.cuh"
 
 namespace bfl {
@@ -105,7 +107,6 @@ struct TcArgs {
     const int32_t* items;   // PARTIAL: triples (row, chunk, scratch slot)
     float* scratch;         // PARTIAL: per slot D*D matrix + D (b) + D (sum q) + 4 (sum w, ...) floats
     int64_t split;          // PARTIAL: chunk length in nnz
-    int loss_axis1;         // compute_loss && axis == 1: also hand over sum q / sum w
 };
 
 template <int D>
@@ -144,7 +145,9 @@ __global__ void tc_scale_kernel(const unsigned int* __restrict__ ymax, const uns
     out[1] = ldexpf(1.f, -2 * e);
 }
 
-template <int D, bool PARTIAL>
+// LOSS1: compute_loss on the item axis (the convert warps also hand sum q / sum w to the epilogue); a template parameter so
+// that the common case keeps a branch-free convert loop
+template <int D, bool PARTIAL, bool LOSS1>
 __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
     static_assert(D == 128 || (D == 256 && PARTIAL), "fused row solve: d = 128; split-row mode: d = 128 or 256");
     constexpr int TILE = Cfg<D>::TILE, NACC = Cfg<D>::NACC, NF = Cfg<D>::NF, LBO = Cfg<D>::LBO;
@@ -236,6 +239,12 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 S.keys[rs][slot] = key;
                 S.sws[rs][slot] = sqrtf(fabsf(w)) * scale;
                 S.wv[rs][slot] = w;
+            } else {   // the lanes without an entry zero the scale / weight of the unused slots cnt .. TILE-1
+                const int zslot = cnt + lane - slot;
+                if (zslot < TILE) {
+                    S.sws[rs][zslot] = 0.f;
+                    S.wv[rs][zslot] = 0.f;
+                }
             }
             if (lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
             __syncwarp();
@@ -351,16 +360,23 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 break;
             }
             const int cnt = (int)(meta & 0xffu);
-            const int slot = is + N_ISSUE * lane;
-            const bool mine = slot < cnt;
             const int nmine = cnt > is ? (cnt - is + N_ISSUE - 1) / N_ISSUE : 0;
-            const int32_t key = mine ? S.keys[rs][slot] : 0;
             if (lane == 0) {
                 if (nmine > 0) mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)nmine * D * 4);
                 else mbar_arrive(&S.raw_full[rs]);
             }
             __syncwarp();
-            if (mine) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
+            // A uniform loop over this warp's slots, one elected lane issuing: unlike a divergent-address copy (ELECT / R2UR /
+            // UBLKCP / branch per lane, ~63 cycles each and serial) the iterations are independent and unrolled, so their
+            // register-to-uniform moves overlap.
+#pragma unroll
+            for (int i = 0; i < (TILE + N_ISSUE - 1) / N_ISSUE; ++i) {
+                const int slot = is + N_ISSUE * i;
+                if (slot < cnt) {
+                    const int32_t key = S.keys[rs][slot];
+                    if (lane == 0) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
+                }
+            }
             if (++rs == NR) { rs = 0; ph ^= 1u; }
         }
     } else if (warp == W_MMA) {
@@ -444,60 +460,54 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             const float* rawp = &S.raw[rs][0];
             unsigned char* hi = &S.op[os][0][0];
             unsigned char* lo = &S.op[os][1][0];
+            // one chunk = 8 consecutive entries k of this thread's feature(s): a 16-byte group of the head and of the tail
+            // slab.  GUARD: the tile is not full -- slots >= cnt hold stale rows (scale and weight 0 from the planner; the
+            // value is zeroed as well so that a stale Inf/NaN cannot leak into an unrelated row).
+            auto chunk = [&](auto guard, const int kc) {
+                constexpr bool GUARD = decltype(guard)::value;
+                const int k0 = kc * 8;
+                const float4 sa = *reinterpret_cast<const float4*>(&S.sws[rs][k0]);
+                const float4 sb = *reinterpret_cast<const float4*>(&S.sws[rs][k0 + 4]);
+                const float4 wa = *reinterpret_cast<const float4*>(&S.wv[rs][k0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&S.wv[rs][k0 + 4]);
+                if (LOSS1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
 #pragma unroll
-            for (int kc = 0; kc < TILE / 8; ++kc) {
-                if (kc < 2 * ksteps) {
-                    const int k0 = kc * 8;
-                    float4 sa = *reinterpret_cast<const float4*>(&S.sws[rs][k0]);
-                    float4 sb = *reinterpret_cast<const float4*>(&S.sws[rs][k0 + 4]);
-                    float4 wa = *reinterpret_cast<const float4*>(&S.wv[rs][k0]);
-                    float4 wb = *reinterpret_cast<const float4*>(&S.wv[rs][k0 + 4]);
-                    const bool full = k0 + 8 <= cnt;      // warp-uniform
-                    if (!full) {   // the stage's slots >= cnt hold stale data: weight and scale 0, value 0
-                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (k0 >= cnt) { sa = z; sb = z; wa = z; wb = z; }
-                        else {
-                            const int r = cnt - k0;   // 1..7 valid
-                            if (r < 2) { sa.y = 0.f; wa.y = 0.f; }
-                            if (r < 3) { sa.z = 0.f; wa.z = 0.f; }
-                            if (r < 4) { sa.w = 0.f; wa.w = 0.f; }
-                            if (r < 5) { sb.x = 0.f; wb.x = 0.f; }
-                            if (r < 6) { sb.y = 0.f; wb.y = 0.f; }
-                            if (r < 7) { sb.z = 0.f; wb.z = 0.f; }
-                            sb.w = 0.f; wb.w = 0.f;
-                        }
+                for (int f = 0; f < NF; ++f) {
+                    const int m = ct + 128 * f;
+                    float q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
+                    if (GUARD) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
                     }
-                    if (ta.loss_axis1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) {
-                        const int m = ct + 128 * f;
-                        float q[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
-                        if (!full) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
-                        }
-                        const float2 q01 = make_float2(q[0], q[1]), q23 = make_float2(q[2], q[3]);
-                        const float2 q45 = make_float2(q[4], q[5]), q67 = make_float2(q[6], q[7]);
-                        uint4 h4, l4;
-                        split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
-                        split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
-                        split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
-                        split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
-                        const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
-                        *reinterpret_cast<uint4*>(hi + off) = h4;
-                        *reinterpret_cast<uint4*>(lo + off) = l4;
-                        bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
-                        bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
-                        bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
-                        bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
-                        if (ta.loss_axis1) {
-                            qacc[f].x += (q[0] + q[2]) + (q[4] + q[6]);
-                            qacc[f].y += (q[1] + q[3]) + (q[5] + q[7]);
-                        }
+                    const float2 q01 = make_float2(q[0], q[1]), q23 = make_float2(q[2], q[3]);
+                    const float2 q45 = make_float2(q[4], q[5]), q67 = make_float2(q[6], q[7]);
+                    uint4 h4, l4;
+                    split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
+                    split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
+                    split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
+                    split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
+                    const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
+                    *reinterpret_cast<uint4*>(hi + off) = h4;
+                    *reinterpret_cast<uint4*>(lo + off) = l4;
+                    bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
+                    bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
+                    bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
+                    bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
+                    if (LOSS1) {
+                        qacc[f].x += (q[0] + q[2]) + (q[4] + q[6]);
+                        qacc[f].y += (q[1] + q[3]) + (q[5] + q[7]);
                     }
                 }
+            };
+            if (cnt == TILE) {   // full tile: straight-line code
+#pragma unroll
+                for (int kc = 0; kc < TILE / 8; ++kc) chunk(std::false_type{}, kc);
+            } else {
+#pragma unroll
+                for (int kc = 0; kc < TILE / 8; ++kc)
+                    if (kc < 2 * ksteps) chunk(std::true_type{}, kc);
             }
             fence_proxy_async_smem();
             mbar_arrive(&S.raw_empty[rs]);
@@ -505,9 +515,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     S.bvec[bslot][ct + 128 * f] = bacc[f].x + bacc[f].y;
-                    if (ta.loss_axis1) S.sumq[bslot][ct + 128 * f] = qacc[f].x + qacc[f].y;
+                    if (LOSS1) S.sumq[bslot][ct + 128 * f] = qacc[f].x + qacc[f].y;
                 }
-                if (ta.loss_axis1 && ct == 0) S.wsum[bslot] = wacc;
+                if (LOSS1 && ct == 0) S.wsum[bslot] = wacc;
                 bslot = (bslot + 1) & (NBV - 1);
             }
             if (ct == 0) S.meta_op[os] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
@@ -572,9 +582,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 }
                 for (int jj = j; jj < D; jj += 128) {
                     atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][jj]);
-                    if (ta.loss_axis1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
+                    if (LOSS1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
                 }
-                if (ta.loss_axis1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
+                if (LOSS1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
                 tc_fence_before();
                 mbar_arrive(&S.acc_empty[acc]);
                 row = nrow; slot = nslot; n = nn;
@@ -817,12 +827,16 @@ int tc_launch_partial(const AlsArgs& a, const int32_t* items, int64_t nitems, fl
     ta.items = items;
     ta.scratch = scratch;
     ta.split = split;
-    ta.loss_axis1 = (a.compute_loss && a.axis == 1) ? 1 : 0;
     BFL_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * scratch_floats<D>() * (size_t)nslots, st));
     const size_t smem = sizeof(Smem<D>);
-    BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<int64_t>(nitems, (int64_t)num_sms);
-    als_tc_kernel<D, true><<<grid, THREADS, smem, st>>>(ta);
+    if (a.compute_loss && a.axis == 1) {
+        BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<D, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_tc_kernel<D, true, true><<<grid, THREADS, smem, st>>>(ta);
+    } else {
+        BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<D, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_tc_kernel<D, true, false><<<grid, THREADS, smem, st>>>(ta);
+    }
     BFL_LAUNCHED();
     return BFL_OK;
 }
@@ -837,11 +851,15 @@ inline int tc_launch(const AlsArgs& a, int num_sms, cudaStream_t st) {
     ta.items = nullptr;
     ta.scratch = nullptr;
     ta.split = 0;
-    ta.loss_axis1 = (a.compute_loss && a.axis == 1) ? 1 : 0;
     const size_t smem = sizeof(Smem<128>);
-    BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<int64_t>(nrows, (int64_t)num_sms);
-    als_tc_kernel<128, false><<<grid, THREADS, smem, st>>>(ta);
+    if (a.compute_loss && a.axis == 1) {
+        BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_tc_kernel<128, false, true><<<grid, THREADS, smem, st>>>(ta);
+    } else {
+        BFL_CUDA(cudaFuncSetAttribute(als_tc_kernel<128, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        als_tc_kernel<128, false, false><<<grid, THREADS, smem, st>>>(ta);
+    }
     BFL_LAUNCHED();
     return BFL_OK;
 }
