@@ -53,11 +53,14 @@ namespace tc {
 
 using namespace sm100;
 
-// 16 warps x 128 registers fill the register file (registers are allocated for warp counts rounded up to 4: a 17th warp
-// would cap every thread at 96 registers and spill the epilogue)
-constexpr int N_ISSUE = 6, N_CONV = 4;
-constexpr int W_PLAN = 0, W_MMA = 1, W_CONV = 4, W_EPI = 8;   // issuers: warps 2, 3, 12..15; epilogue warp 8 + q owns lane quarter q
-constexpr int WARPS = 16, THREADS = WARPS * 32;
+// 14 warps: epilogue 0..3 (warp q owns tensor-memory lane quarter q), planner 4, MMA issue 5, convert 6..13 (two sets of four:
+// each set takes half of a tile's entries)
+constexpr int N_CONV = 8, KH = N_CONV / 4;
+constexpr int W_EPI = 0, W_PLAN = 4, W_MMA = 5, W_CONV = 6;
+constexpr int WARPS = W_CONV + N_CONV, THREADS = WARPS * 32;
+constexpr int GATHER_AHEAD = 4;   // tiles between a convert warp's gather issue and its use of the tile (<= NR - 2: the raw stage a
+                                  // gather refills was released two iterations ago, so no warp waits for its slowest sibling)
+constexpr int NP = 16;            // gather-plan ring (small slots): the planner runs up to NP tiles ahead, off the critical path
 constexpr int NXS = 8;     // x buffers of the epilogue pipeline (a fast warp publishes row r + 1 while a slow one reads row r - 3)
 constexpr int NR = 6;      // raw stages
 constexpr int NO = 4;      // operand stages
@@ -82,19 +85,19 @@ struct Smem {
     // operand slab: element (feature m, entry k) at byte (k/8)*LBO + (m/8)*128 + (m%8)*16 + (k%8)*2
     alignas(1024) unsigned char op[NO][2][Cfg<D>::OP_BYTES];   // [head|tail]
     alignas(128) float raw[NR][TILE * D];              // gathered rows, pitch D
-    alignas(16) float bvec[NBV][D];                    // b = sum w q
-    alignas(16) float sumq[NBV][D];                    // sum q (loss only)
+    alignas(16) float bvec[NBV][KH][D];                // b = sum w q (one partial per convert set)
+    alignas(16) float sumq[NBV][KH][D];                // sum q (loss only)
     alignas(16) float xs[NXS][D];                      // 128-bit reads: every vector below is 16-byte aligned
     alignas(16) float pv[4][32];                       // CG direction of the warp that owns the block
     alignas(16) float dl[NACC_MAX][4][32];             // [row slot][block]: the block's solution delta
-    alignas(16) float sws[NR][TILE];                   // gather plan: 2^e sqrt|w| per slot
-    alignas(16) float wv[NR][TILE];                    //              w per slot
-    alignas(16) int32_t keys[NR][TILE];                //              gathered row per slot
-    float wsum[NBV];                                   // sum w (loss only)
-    uint32_t meta_raw[NR];
+    alignas(16) float sws[NP][TILE];                   // gather plan: 2^e sqrt|w| per slot
+    alignas(16) float wv[NP][TILE];                    //              w per slot
+    alignas(16) int32_t keys[NP][TILE];                //              gathered row per slot
+    float wsum[NBV][KH];                               // sum w (loss only)
+    uint32_t meta_raw[NP];                             //              count | flags
     uint32_t meta_op[NO];
     int badrow[NXS];
-    alignas(8) uint64_t plan_full[NR], raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO];
+    alignas(8) uint64_t plan_full[NP], plan_empty[NP], raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO];
     alignas(8) uint64_t acc_full[NACC_MAX], acc_empty[NACC_MAX], x_full[NXS], d_full[NACC_MAX][4];
     uint32_t tmem_base;
 };
@@ -107,6 +110,7 @@ struct TcArgs {
     const int32_t* items;   // PARTIAL: triples (row, chunk, scratch slot)
     float* scratch;         // PARTIAL: per slot D*D matrix + D (b) + D (sum q) + 4 (sum w, ...) floats
     int64_t split;          // PARTIAL: chunk length in nnz
+    int debug;              // BFL_TC_DEBUG (timing experiments only; results are wrong): 1 no gathers, 2 no MMAs, 4 no convert math, 8 no epilogue math
 };
 
 template <int D>
@@ -159,21 +163,26 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 
     if (tid == 0) {
         for (int i = 0; i < NR; ++i) {
+            // every barrier counts WARPS, not threads: an arrive executed by 32 lanes is 32 serial barrier updates, and with
+            // per-thread arrivals the hand-offs alone cost ~700 cycles per tile (measured with all the math switched off)
+            mbar_init(&S.raw_full[i], N_CONV);
+            mbar_init(&S.raw_empty[i], N_CONV);
+        }
+        for (int i = 0; i < NP; ++i) {
             mbar_init(&S.plan_full[i], 1);
-            mbar_init(&S.raw_full[i], N_ISSUE);
-            mbar_init(&S.raw_empty[i], N_CONV * 32);
+            mbar_init(&S.plan_empty[i], N_CONV);
         }
         for (int i = 0; i < NO; ++i) {
-            mbar_init(&S.op_full[i], N_CONV * 32);
+            mbar_init(&S.op_full[i], N_CONV);
             mbar_init(&S.op_empty[i], 1);
         }
         for (int i = 0; i < NACC; ++i) {
             mbar_init(&S.acc_full[i], 1);
-            mbar_init(&S.acc_empty[i], 128);
+            mbar_init(&S.acc_empty[i], 4);
             for (int b = 0; b < 4; ++b) mbar_init(&S.d_full[i][b], 1);
         }
         for (int i = 0; i < NXS; ++i) {
-            mbar_init(&S.x_full[i], 128);
+            mbar_init(&S.x_full[i], 4);
             S.badrow[i] = 0;
         }
         mbar_init_fence();
@@ -230,11 +239,11 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 
     if (warp == W_PLAN) {
         // ================= planner: gather plans =================
-        uint32_t rs = 0, rph = 0;   // stage, phase of raw_empty
+        uint32_t rs = 0, rph = 0;   // plan slot, phase of plan_empty
         auto emit = [&](unsigned mask, uint32_t flags, int32_t key, float w) {
             const int cnt = __popc(mask);
             const int slot = __popc(mask & ((1u << lane) - 1u));
-            mbar_wait(&S.raw_empty[rs], rph ^ 1u);
+            mbar_wait(&S.plan_empty[rs], rph ^ 1u);
             if ((mask >> lane) & 1u) {
                 S.keys[rs][slot] = key;
                 S.sws[rs][slot] = sqrtf(fabsf(w)) * scale;
@@ -249,13 +258,16 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             if (lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.plan_full[rs]);
-            if (++rs == NR) { rs = 0; rph ^= 1u; }
+            if (++rs == NP) { rs = 0; rph ^= 1u; }
         };
         // Software pipeline over the CTA's items.  Every level of the dependent load chain  item -> row offsets -> entries
         // is issued whole rows ahead of its use (a gathered tile takes ~700 cycles to issue, a global load ~1-2 thousand
         // cycles under load: with a one-tile look-ahead every tile paid that latency):
         //   item i+4: row id            item i+3: offsets            item i+2: first super-chunk of entries (keys, weights)
         // and inside a long row the next super-chunk (SC tiles) is loaded while the current one is being emitted.
+        // The planner is one warp on the critical path of every tile (with all the math switched off the kernel still
+        // needed ~1000 cycles per tile for the plan hand-offs alone): inside a row everything is 32-bit, and a super-chunk
+        // without negative weights -- the normal case -- takes the short path: slot == lane, no ballots, no prefix sums.
         constexpr int SC = 4, SCN = SC * TILE;
         const bool inl = lane < TILE;
         auto load_id = [&](int64_t it, int& row, int& chunk) {
@@ -271,68 +283,99 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 }
             }
         };
-        auto load_span = [&](int row, int chunk, int64_t& beg, int64_t& n) {
-            beg = 0;
+        auto load_span = [&](int row, int chunk, const int32_t*& kp, const float*& vp, int& n) {
+            kp = a.keys;
+            vp = a.vals;
             n = 0;
             if (row >= 0) {
                 const int64_t rb = row == 0 ? 0 : a.indptr[row - 1];
                 const int64_t rn = a.indptr[row] - rb;
+                int64_t beg = rb;
+                n = (int)rn;            // fused rows are binned below 2^31 entries, chunks are `split` long
                 if (PARTIAL) {
                     beg = rb + (int64_t)chunk * ta.split;
-                    n = min(ta.split, rn - (int64_t)chunk * ta.split);
-                } else {
-                    beg = rb;
-                    n = rn;
+                    n = (int)min(ta.split, rn - (int64_t)chunk * ta.split);
+                }
+                kp = a.keys + (beg - a.shift);
+                vp = a.vals + (beg - a.shift);
+            }
+        };
+        auto load_sc = [&](const int32_t* kp, const float* vp, int n, int c0, int32_t (&key)[SC], float (&w)[SC]) {
+#pragma unroll
+            for (int s = 0; s < SC; ++s) {
+                const int idx = c0 + s * TILE + lane;
+                const bool ok = inl && idx < n;
+                key[s] = ok ? kp[idx] : 0;
+                w[s] = ok ? vp[idx] * a.alpha : 0.f;
+            }
+        };
+        auto emit_sc = [&](int n, int c0, const int32_t (&key)[SC], const float (&w)[SC]) {
+            bool neg = false;
+#pragma unroll
+            for (int s = 0; s < SC; ++s) neg |= w[s] < 0.f;
+            if (!__any_sync(FULL, neg)) {
+#pragma unroll
+                for (int s = 0; s < SC; ++s) {
+                    const int t0 = c0 + s * TILE;
+                    if (t0 < n) {
+                        const uint32_t meta = (uint32_t)min(TILE, n - t0) | (t0 == 0 ? F_FIRST : 0u) | (t0 + TILE >= n ? F_LAST : 0u);
+                        mbar_wait(&S.plan_empty[rs], rph ^ 1u);
+                        if (inl) {   // lanes beyond the row's end carry key 0, weight 0: the unused slots are zero-filled
+                            float sq;
+                            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(w[s]));
+                            S.keys[rs][lane] = key[s];
+                            S.sws[rs][lane] = sq * scale;
+                            S.wv[rs][lane] = w[s];
+                        }
+                        if (lane == 0) S.meta_raw[rs] = meta;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.plan_full[rs]);
+                        if (++rs == NP) { rs = 0; rph ^= 1u; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int s = 0; s < SC; ++s) {
+                    const int t0 = c0 + s * TILE;
+                    if (t0 < n) {
+                        const bool valid = inl && t0 + lane < n;
+                        const unsigned pm = __ballot_sync(FULL, valid && !(w[s] < 0.f));
+                        const unsigned nm = __ballot_sync(FULL, valid && (w[s] < 0.f));
+                        const bool lastc = t0 + TILE >= n;
+                        uint32_t fl = (t0 == 0 ? F_FIRST : 0u);
+                        if (pm) {
+                            emit(pm, fl | ((lastc && !nm) ? F_LAST : 0u), key[s], w[s]);
+                            fl = 0u;
+                        }
+                        if (nm) emit(nm, fl | F_NEG | (lastc ? F_LAST : 0u), key[s], w[s]);
+                    }
                 }
             }
         };
-        auto load_sc = [&](int64_t beg, int64_t n, int64_t c0, int32_t (&key)[SC], float (&w)[SC]) {
-#pragma unroll
-            for (int s = 0; s < SC; ++s) {
-                const int64_t idx = c0 + s * TILE + lane;
-                const bool ok = inl && idx < n;
-                key[s] = ok ? a.keys[beg - a.shift + idx] : 0;
-                w[s] = ok ? a.vals[beg - a.shift + idx] * a.alpha : 0.f;
-            }
-        };
-        int64_t beg0, n0, beg1, n1, beg2, n2, beg3, n3;
+        const int32_t *kp0, *kp1, *kp2, *kp3;
+        const float *vp0, *vp1, *vp2, *vp3;
+        int n0, n1, n2, n3;
         int row_t, ch_t, row4, ch4;
         int32_t k0[SC], k1[SC], k2[SC], nk[SC];
         float w0[SC], w1[SC], w2[SC], nw[SC];
         load_id(my_first, row_t, ch_t);
-        load_span(row_t, ch_t, beg0, n0);
-        load_sc(beg0, n0, 0, k0, w0);
+        load_span(row_t, ch_t, kp0, vp0, n0);
+        load_sc(kp0, vp0, n0, 0, k0, w0);
         load_id(my_first + stride, row_t, ch_t);
-        load_span(row_t, ch_t, beg1, n1);
-        load_sc(beg1, n1, 0, k1, w1);
+        load_span(row_t, ch_t, kp1, vp1, n1);
+        load_sc(kp1, vp1, n1, 0, k1, w1);
         load_id(my_first + 2 * stride, row_t, ch_t);
-        load_span(row_t, ch_t, beg2, n2);
+        load_span(row_t, ch_t, kp2, vp2, n2);
         load_id(my_first + 3 * stride, row4, ch4);
         for (int64_t it = my_first; it < nitems; it += stride) {
             // issue the look-ahead loads (their results are first touched one item later)
-            load_sc(beg2, n2, 0, k2, w2);
-            load_span(row4, ch4, beg3, n3);
+            load_sc(kp2, vp2, n2, 0, k2, w2);
+            load_span(row4, ch4, kp3, vp3, n3);
             load_id(it + 4 * stride, row4, ch4);
-            for (int64_t c0 = 0; c0 < n0; c0 += SCN) {
+            for (int c0 = 0; c0 < n0; c0 += SCN) {
                 const bool more = c0 + SCN < n0;
-                if (more) load_sc(beg0, n0, c0 + SCN, nk, nw);
-#pragma unroll
-                for (int s = 0; s < SC; ++s) {
-                    const int64_t t0 = c0 + s * TILE;
-                    if (t0 < n0) {
-                        const float w = w0[s];
-                        const bool valid = inl && t0 + lane < n0;
-                        const unsigned pm = __ballot_sync(FULL, valid && !(w < 0.f));
-                        const unsigned nm = __ballot_sync(FULL, valid && (w < 0.f));
-                        const bool lastc = t0 + TILE >= n0;
-                        uint32_t fl = (t0 == 0 ? F_FIRST : 0u);
-                        if (pm) {
-                            emit(pm, fl | ((lastc && !nm) ? F_LAST : 0u), k0[s], w);
-                            fl = 0u;
-                        }
-                        if (nm) emit(nm, fl | F_NEG | (lastc ? F_LAST : 0u), k0[s], w);
-                    }
-                }
+                if (more) load_sc(kp0, vp0, n0, c0 + SCN, nk, nw);
+                emit_sc(n0, c0, k0, w0);
                 if (more) {
 #pragma unroll
                     for (int s = 0; s < SC; ++s) { k0[s] = nk[s]; w0[s] = nw[s]; }
@@ -340,44 +383,13 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
 #pragma unroll
             for (int s = 0; s < SC; ++s) { k0[s] = k1[s]; w0[s] = w1[s]; k1[s] = k2[s]; w1[s] = w2[s]; }
-            beg0 = beg1; n0 = n1; beg1 = beg2; n1 = n2; beg2 = beg3; n2 = n3;
+            kp0 = kp1; vp0 = vp1; n0 = n1; kp1 = kp2; vp1 = vp2; n1 = n2; kp2 = kp3; vp2 = vp3; n2 = n3;
         }
         // stop marker
-        mbar_wait(&S.raw_empty[rs], rph ^ 1u);
+        mbar_wait(&S.plan_empty[rs], rph ^ 1u);
         if (lane == 0) {
             S.meta_raw[rs] = F_STOP;
             mbar_arrive(&S.plan_full[rs]);
-        }
-    } else if (warp == 2 || warp == 3 || warp >= W_EPI + 4) {
-        // ================= issuers: plan -> bulk copies =================
-        const int is = warp < 4 ? warp - 2 : warp - (W_EPI + 4) + 2;   // 0..5; issuer `is` copies the slots is, is + 6, ...
-        uint32_t rs = 0, ph = 0;
-        for (;;) {
-            mbar_wait(&S.plan_full[rs], ph);
-            const uint32_t meta = S.meta_raw[rs];
-            if (meta & F_STOP) {
-                if (lane == 0) mbar_arrive(&S.raw_full[rs]);
-                break;
-            }
-            const int cnt = (int)(meta & 0xffu);
-            const int nmine = cnt > is ? (cnt - is + N_ISSUE - 1) / N_ISSUE : 0;
-            if (lane == 0) {
-                if (nmine > 0) mbar_arrive_expect_tx(&S.raw_full[rs], (uint32_t)nmine * D * 4);
-                else mbar_arrive(&S.raw_full[rs]);
-            }
-            __syncwarp();
-            // A uniform loop over this warp's slots, one elected lane issuing: unlike a divergent-address copy (ELECT / R2UR /
-            // UBLKCP / branch per lane, ~63 cycles each and serial) the iterations are independent and unrolled, so their
-            // register-to-uniform moves overlap.
-#pragma unroll
-            for (int i = 0; i < (TILE + N_ISSUE - 1) / N_ISSUE; ++i) {
-                const int slot = is + N_ISSUE * i;
-                if (slot < cnt) {
-                    const int32_t key = S.keys[rs][slot];
-                    if (lane == 0) bulk_g2s(&S.raw[rs][slot * D], a.Y + (int64_t)key * a.ld, D * 4, &S.raw_full[rs]);
-                }
-            }
-            if (++rs == NR) { rs = 0; ph ^= 1u; }
         }
     } else if (warp == W_MMA) {
         // ================= MMA issue =================
@@ -398,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 const int ksteps = (int)(meta & 0xffu);
                 const uint32_t neg = (meta & F_NEG) ? IDESC_NEGATE_A : 0u;
                 const uint32_t hi = s32(&S.op[os][0][0]), lo = s32(&S.op[os][1][0]);
-                for (int ks = 0; ks < ksteps; ++ks) {
+                for (int ks = 0; ks < ((ta.debug & 2) ? 0 : ksteps); ++ks) {
                     const uint32_t acc0 = (row_open || ks > 0) ? 1u : 0u;
                     // K = 16 = two 8-k chunks: LBO apart; neighbouring 8-feature core matrices 128 B apart (SBO)
                     const uint64_t dh = smem_desc(hi + ks * 2 * LBO, LBO, 128);
@@ -436,19 +448,66 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         // ================= convert: raw fp32 -> scaled fp16 head/tail operand slabs =================
         // thread ct owns features m = ct + 128 f: a warp reads 32 consecutive floats of one gathered row (conflict-free)
         // and writes 32 consecutive 16-byte groups of a core-matrix column (conflict-free).
-        const int ct = tid - W_CONV * 32;
+        const int cta = tid - W_CONV * 32;
+        const int ct = cta & 127;          // feature(s) of this thread
+        const int kh = cta >> 7;           // which part of a tile's entries this convert set takes
+        constexpr int CHS = TILE / 8 / KH; // 8-entry chunks per tile and set
         uint32_t rs = 0, rph = 0, os = 0, oph = 0, bslot = 0;
         float2 bacc[NF], qacc[NF];
         float wacc = 0.f;
 #pragma unroll
         for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
+        // Gathers.  The convert warps issue the tile gathers themselves, GATHER_AHEAD tiles before they consume the tile:
+        // warp cw copies the TILE / 8 rows cw, cw + 8, ... of a planned tile with one coalesced 16-byte-per-lane cp.async per
+        // 512 bytes (SASS LDGSTS; a whole warp instruction moves a full row segment, and the issue cost is spread over
+        // eight warps that have issue slots to spare -- the 512-byte TMA bulk copies this replaces cost ~63-100 issue
+        // cycles each in a dedicated warp) as one commit group per tile; before converting tile t a warp
+        // waits for its own group of tile t (cp.async.wait_group) and posts one arrival on the tile's mbarrier.
+        const int cw = cta >> 5;
+        uint32_t gs = 0, gph = 0, grs = 0, grph = 0;   // plan slot / raw stage of the next tile to gather
+        bool plan_end = false;
+        auto gather = [&]() {
+            if (plan_end) {
+                cp_async_commit();   // keep one commit group per iteration so that wait_group counts tiles to the very end
+                return;
+            }
+            mbar_wait(&S.plan_full[gs], gph);
+            const uint32_t gmeta = S.meta_raw[gs];
+            mbar_wait(&S.raw_empty[grs], grph ^ 1u);   // every convert warp is done with the tile that used this stage
+            if (gmeta & F_STOP) {
+                plan_end = true;
+            } else {
+                const int gcnt = (ta.debug & 1) ? 0 : (int)(gmeta & 0xffu);
+#pragma unroll
+                for (int i = 0; i < TILE / 8; ++i) {
+                    const int slot = cw + 8 * i;
+                    if (slot < gcnt) {
+                        const float* src = a.Y + (int64_t)S.keys[gs][slot] * a.ld + lane * 4;
+                        float* dst = &S.raw[grs][slot * D + lane * 4];
+#pragma unroll
+                        for (int c = 0; c < D / 128; ++c) cp_async16_cg(dst + c * 128, src + c * 128);
+                    }
+                }
+            }
+            cp_async_commit();
+            if (++gs == NP) { gs = 0; gph ^= 1u; }
+            if (++grs == NR) { grs = 0; grph ^= 1u; }
+        };
+        uint32_t cs = 0;   // plan slot of the tile being converted
+#pragma unroll 1
+        for (int i = 0; i < GATHER_AHEAD; ++i) gather();
         for (;;) {
-            mbar_wait(&S.raw_full[rs], rph);
-            const uint32_t meta = S.meta_raw[rs];
+            gather();
+            cp_async_wait_group<GATHER_AHEAD>();   // this warp's rows of the tile about to be converted have landed
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.raw_full[rs]);
+            mbar_wait(&S.raw_full[rs], rph);        // ... and everybody else's
+            const uint32_t meta = S.meta_raw[cs];
             mbar_wait(&S.op_empty[os], oph ^ 1u);
             if (meta & F_STOP) {
-                if (ct == 0) S.meta_op[os] = F_STOP;
-                mbar_arrive(&S.op_full[os]);
+                if (cta == 0) S.meta_op[os] = F_STOP;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.op_full[os]);
                 break;
             }
             const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 15) >> 4;
@@ -466,10 +525,10 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             auto chunk = [&](auto guard, const int kc) {
                 constexpr bool GUARD = decltype(guard)::value;
                 const int k0 = kc * 8;
-                const float4 sa = *reinterpret_cast<const float4*>(&S.sws[rs][k0]);
-                const float4 sb = *reinterpret_cast<const float4*>(&S.sws[rs][k0 + 4]);
-                const float4 wa = *reinterpret_cast<const float4*>(&S.wv[rs][k0]);
-                const float4 wb = *reinterpret_cast<const float4*>(&S.wv[rs][k0 + 4]);
+                const float4 sa = *reinterpret_cast<const float4*>(&S.sws[cs][k0]);
+                const float4 sb = *reinterpret_cast<const float4*>(&S.sws[cs][k0 + 4]);
+                const float4 wa = *reinterpret_cast<const float4*>(&S.wv[cs][k0]);
+                const float4 wb = *reinterpret_cast<const float4*>(&S.wv[cs][k0 + 4]);
                 if (LOSS1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
@@ -501,27 +560,33 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     }
                 }
             };
-            if (cnt == TILE) {   // full tile: straight-line code
+            if (ta.debug & 4) {
+            } else if (cnt == TILE) {   // full tile: straight-line code
 #pragma unroll
-                for (int kc = 0; kc < TILE / 8; ++kc) chunk(std::false_type{}, kc);
+                for (int c = 0; c < CHS; ++c) chunk(std::false_type{}, kh * CHS + c);
             } else {
 #pragma unroll
-                for (int kc = 0; kc < TILE / 8; ++kc)
-                    if (kc < 2 * ksteps) chunk(std::true_type{}, kc);
+                for (int c = 0; c < CHS; ++c)
+                    if (kh * CHS + c < 2 * ksteps) chunk(std::true_type{}, kh * CHS + c);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(&S.raw_empty[rs]);
+            fence_proxy_async_smem();     // this thread's operand stores -> visible to the tensor core's (async proxy) reads
             if (meta & F_LAST) {
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    S.bvec[bslot][ct + 128 * f] = bacc[f].x + bacc[f].y;
-                    if (LOSS1) S.sumq[bslot][ct + 128 * f] = qacc[f].x + qacc[f].y;
+                    S.bvec[bslot][kh][ct + 128 * f] = bacc[f].x + bacc[f].y;
+                    if (LOSS1) S.sumq[bslot][kh][ct + 128 * f] = qacc[f].x + qacc[f].y;
                 }
-                if (LOSS1 && ct == 0) S.wsum[bslot] = wacc;
+                if (LOSS1 && ct == 0) S.wsum[bslot][kh] = wacc;
                 bslot = (bslot + 1) & (NBV - 1);
             }
-            if (ct == 0) S.meta_op[os] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
-            mbar_arrive(&S.op_full[os]);
+            if (cta == 0) S.meta_op[os] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
+            __syncwarp();
+            if (lane == 0) {   // one arrival per warp on each of the three hand-offs of a tile
+                mbar_arrive(&S.raw_empty[rs]);
+                mbar_arrive(&S.plan_empty[cs]);
+                mbar_arrive(&S.op_full[os]);
+            }
+            cs = (cs + 1) & (NP - 1);
             if (++rs == NR) { rs = 0; rph ^= 1u; }
             if (++os == NO) { os = 0; oph ^= 1u; }
         }
@@ -581,12 +646,13 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     }
                 }
                 for (int jj = j; jj < D; jj += 128) {
-                    atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][jj]);
-                    if (LOSS1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][jj]);
+                    atomicAdd(sc + (size_t)D * D + jj, S.bvec[bs][0][jj] + (KH == 2 ? S.bvec[bs][KH - 1][jj] : 0.f));
+                    if (LOSS1) atomicAdd(sc + (size_t)D * D + D + jj, S.sumq[bs][0][jj] + (KH == 2 ? S.sumq[bs][KH - 1][jj] : 0.f));
                 }
-                if (LOSS1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs]);
+                if (LOSS1 && j == 0) atomicAdd(sc + (size_t)D * D + 2 * D, S.wsum[bs][0] + (KH == 2 ? S.wsum[bs][KH - 1] : 0.f));
                 tc_fence_before();
-                mbar_arrive(&S.acc_empty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.acc_empty[acc]);
                 row = nrow; slot = nslot; n = nn;
             }
         } else {
@@ -606,7 +672,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             float nlen = len_of(row), nlen1 = len_of(row1);
             if (row >= 0) {   // publish row 0's x
                 S.xs[0][j] = xj;
-                mbar_arrive(&S.x_full[0]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.x_full[0]);
             }
             for (int64_t seq = 0; row >= 0; ++seq) {
                 // look-ahead loads
@@ -615,7 +682,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 const float nlen2 = len_of(row2);
                 if (row1 >= 0) {   // publish the next row's x: by the time a warp gets there everybody has
                     S.xs[(seq + 1) & (NXS - 1)][j] = x1;
-                    mbar_arrive(&S.x_full[(seq + 1) & (NXS - 1)]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.x_full[(seq + 1) & (NXS - 1)]);
                 }
                 const uint32_t acc = (uint32_t)(seq % NACC), aph = (uint32_t)((seq / NACC) & 1);
                 const uint32_t bs = (uint32_t)(seq & (NBV - 1));
@@ -624,8 +692,16 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 mbar_wait(&S.x_full[xsl], (uint32_t)((seq / NXS) & 1));
                 mbar_wait(&S.acc_full[acc], aph);
                 tc_fence_after();
+                if (ta.debug & 8) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.acc_empty[acc]);
+                    row = row1; row1 = row2; row2 = row3;
+                    xj = x1; x1 = x2;
+                    continue;
+                }
                 const uint32_t dbase = tmem + lane_off + 128 * (1 + acc);
-                const float bj = S.bvec[bs][j];
+                const float bj = S.bvec[bs][0][j] + (KH == 2 ? S.bvec[bs][KH - 1][j] : 0.f);
                 // ---- h = (G + reg I) x + 2^-2e A x - b  (A = the accumulator); keep the diagonal block of M in registers ----
                 float hG = 0.f, hD = 0.f;
                 float md[32];
@@ -659,9 +735,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     double t = (double)(kappa * a.reg * xj * xj);
                     if (a.axis == 1) {
                         t += (double)xj * (double)(hG - a.reg * xj) + (double)xj * (double)hD -
-                             2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][j]);
+                             2.0 * (double)xj * ((double)bj + (double)S.sumq[bs][0][j] + (KH == 2 ? (double)S.sumq[bs][KH - 1][j] : 0.0));
                         if (j == 0) {
-                            const double ws = (double)S.wsum[bs];
+                            const double ws = (double)S.wsum[bs][0] + (KH == 2 ? (double)S.wsum[bs][KH - 1] : 0.0);
                             t += (double)nlen + ws;
                             l_deno += (double)a.Y_rows + ws;
                         }
@@ -690,7 +766,8 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 }
                 // this warp's reads of the accumulator are done
                 tc_fence_before();
-                mbar_arrive(&S.acc_empty[acc]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.acc_empty[acc]);
                 // ---- 3-step CG on the own diagonal block (als.cc:324-345) ----
                 float xv = 0.f;
                 {
@@ -827,6 +904,7 @@ int tc_launch_partial(const AlsArgs& a, const int32_t* items, int64_t nitems, fl
     ta.items = items;
     ta.scratch = scratch;
     ta.split = split;
+    ta.debug = 0;
     BFL_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * scratch_floats<D>() * (size_t)nslots, st));
     const size_t smem = sizeof(Smem<D>);
     const int grid = (int)std::min<int64_t>(nitems, (int64_t)num_sms);
@@ -851,6 +929,7 @@ inline int tc_launch(const AlsArgs& a, int num_sms, cudaStream_t st) {
     ta.items = nullptr;
     ta.scratch = nullptr;
     ta.split = 0;
+    ta.debug = getenv("BFL_TC_DEBUG") ? atoi(getenv("BFL_TC_DEBUG")) : 0;
     const size_t smem = sizeof(Smem<128>);
     const int grid = (int)std::min<int64_t>(nrows, (int64_t)num_sms);
     if (a.compute_loss && a.axis == 1) {

@@ -49,6 +49,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
                  : "memory");
 }
 
+// ---- 16-byte cp.async (SASS LDGSTS), completion counted on an mbarrier -------------------------------
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// waits until at most N of the executing thread's most recent commit groups are still pending
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- tensor memory ----------------------------------------------------------------------------
 // whole warp; ncols: power of two in [32, 512]; the base address is written to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
