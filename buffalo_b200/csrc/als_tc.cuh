@@ -58,12 +58,14 @@ using namespace sm100;
 constexpr int N_CONV = 8, KH = N_CONV / 4;
 constexpr int W_EPI = 0, W_PLAN = 4, W_MMA = 5, W_CONV = 6;
 constexpr int WARPS = W_CONV + N_CONV, THREADS = WARPS * 32;
-constexpr int GATHER_AHEAD = 4;   // tiles between a convert warp's gather issue and its use of the tile (<= NR - 2: the raw stage a
-                                  // gather refills was released two iterations ago, so no warp waits for its slowest sibling)
-constexpr int NP = 16;            // gather-plan ring (small slots): the planner runs up to NP tiles ahead, off the critical path
 constexpr int NXS = 8;     // x buffers of the epilogue pipeline (a fast warp publishes row r + 1 while a slow one reads row r - 3)
-constexpr int NR = 6;      // raw stages
-constexpr int NO = 4;      // operand stages
+// Hand-offs are per GROUP of PT consecutive tiles of the CTA's tile stream (a group may span rows: every tile carries its own
+// flags): with all the math switched off the barrier round trips of a one-tile hand-off still cost ~700 cycles per tile.
+constexpr int PT = 2;      // tiles per hand-off group
+constexpr int NR = 3;      // raw stages (groups)
+constexpr int NO = 2;      // operand stages (groups)
+constexpr int GATHER_AHEAD = 2;   // groups between a convert warp's gather issue and its use of the group (< NR)
+constexpr int NPG = 8, NP = NPG * PT;   // gather-plan ring (small slots): the planner runs up to NPG groups ahead
 constexpr int NBV = 8;     // ring of per-row vectors handed from the convert warps to the epilogue
 // d = 128: 32 gathered rows per stage, three 128-column accumulators (fused solve) behind the resident G + reg I;
 // d = 256 (split-row mode only): 16 rows per stage, one accumulator set of 384 columns: rows 0..127 x all 256 columns
@@ -83,8 +85,8 @@ template <int D>
 struct Smem {
     static constexpr int TILE = Cfg<D>::TILE;
     // operand slab: element (feature m, entry k) at byte (k/8)*LBO + (m/8)*128 + (m%8)*16 + (k%8)*2
-    alignas(1024) unsigned char op[NO][2][Cfg<D>::OP_BYTES];   // [head|tail]
-    alignas(128) float raw[NR][TILE * D];              // gathered rows, pitch D
+    alignas(1024) unsigned char op[NO][PT][2][Cfg<D>::OP_BYTES];   // [stage][tile of the group][head|tail]
+    alignas(128) float raw[NR][PT][TILE * D];          // gathered rows, pitch D
     alignas(16) float bvec[NBV][KH][D];                // b = sum w q (one partial per convert set)
     alignas(16) float sumq[NBV][KH][D];                // sum q (loss only)
     alignas(16) float xs[NXS][D];                      // 128-bit reads: every vector below is 16-byte aligned
@@ -95,9 +97,9 @@ struct Smem {
     alignas(16) int32_t keys[NP][TILE];                //              gathered row per slot
     float wsum[NBV][KH];                               // sum w (loss only)
     uint32_t meta_raw[NP];                             //              count | flags
-    uint32_t meta_op[NO];
+    uint32_t meta_op[NO][PT];
     int badrow[NXS];
-    alignas(8) uint64_t plan_full[NP], plan_empty[NP], raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO];
+    alignas(8) uint64_t plan_full[NPG], plan_empty[NPG], raw_full[NR], raw_empty[NR], op_full[NO], op_empty[NO];
     alignas(8) uint64_t acc_full[NACC_MAX], acc_empty[NACC_MAX], x_full[NXS], d_full[NACC_MAX][4];
     uint32_t tmem_base;
 };
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             mbar_init(&S.raw_full[i], N_CONV);
             mbar_init(&S.raw_empty[i], N_CONV);
         }
-        for (int i = 0; i < NP; ++i) {
+        for (int i = 0; i < NPG; ++i) {
             mbar_init(&S.plan_full[i], 1);
             mbar_init(&S.plan_empty[i], N_CONV);
         }
@@ -239,11 +241,24 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
 
     if (warp == W_PLAN) {
         // ================= planner: gather plans =================
-        uint32_t rs = 0, rph = 0;   // plan slot, phase of plan_empty
+        uint32_t gsl = 0, rph = 0, pe = 0;   // group slot, phase of plan_empty, tile within the group
+        // begin a tile: its plan slot (the group's slots are claimed when its first tile starts)
+        auto tile_begin = [&]() -> uint32_t {
+            if (pe == 0) mbar_wait(&S.plan_empty[gsl], rph ^ 1u);
+            return gsl * PT + pe;
+        };
+        // finish a tile (after __syncwarp): the group is published with its last tile
+        auto tile_end = [&]() {
+            if (++pe == PT) {
+                if (lane == 0) mbar_arrive(&S.plan_full[gsl]);
+                pe = 0;
+                if (++gsl == NPG) { gsl = 0; rph ^= 1u; }
+            }
+        };
         auto emit = [&](unsigned mask, uint32_t flags, int32_t key, float w) {
             const int cnt = __popc(mask);
             const int slot = __popc(mask & ((1u << lane) - 1u));
-            mbar_wait(&S.plan_empty[rs], rph ^ 1u);
+            const uint32_t rs = tile_begin();
             if ((mask >> lane) & 1u) {
                 S.keys[rs][slot] = key;
                 S.sws[rs][slot] = sqrtf(fabsf(w)) * scale;
@@ -257,8 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
             if (lane == 0) S.meta_raw[rs] = (uint32_t)cnt | flags;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&S.plan_full[rs]);
-            if (++rs == NP) { rs = 0; rph ^= 1u; }
+            tile_end();
         };
         // Software pipeline over the CTA's items.  Every level of the dependent load chain  item -> row offsets -> entries
         // is issued whole rows ahead of its use (a gathered tile takes ~700 cycles to issue, a global load ~1-2 thousand
@@ -319,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     const int t0 = c0 + s * TILE;
                     if (t0 < n) {
                         const uint32_t meta = (uint32_t)min(TILE, n - t0) | (t0 == 0 ? F_FIRST : 0u) | (t0 + TILE >= n ? F_LAST : 0u);
-                        mbar_wait(&S.plan_empty[rs], rph ^ 1u);
+                        const uint32_t rs = tile_begin();
                         if (inl) {   // lanes beyond the row's end carry key 0, weight 0: the unused slots are zero-filled
                             float sq;
                             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sq) : "f"(w[s]));
@@ -329,8 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         }
                         if (lane == 0) S.meta_raw[rs] = meta;
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.plan_full[rs]);
-                        if (++rs == NP) { rs = 0; rph ^= 1u; }
+                        tile_end();
                     }
                 }
             } else {
@@ -385,63 +398,71 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             for (int s = 0; s < SC; ++s) { k0[s] = k1[s]; w0[s] = w1[s]; k1[s] = k2[s]; w1[s] = w2[s]; }
             kp0 = kp1; vp0 = vp1; n0 = n1; kp1 = kp2; vp1 = vp2; n1 = n2; kp2 = kp3; vp2 = vp3; n2 = n3;
         }
-        // stop marker
-        mbar_wait(&S.plan_empty[rs], rph ^ 1u);
-        if (lane == 0) {
-            S.meta_raw[rs] = F_STOP;
-            mbar_arrive(&S.plan_full[rs]);
-        }
+        // stop marker: fills the rest of the current group (or one more group)
+        do {
+            const uint32_t rs = tile_begin();
+            if (lane == 0) S.meta_raw[rs] = F_STOP;
+            __syncwarp();
+            tile_end();
+        } while (pe != 0);
     } else if (warp == W_MMA) {
         // ================= MMA issue =================
         uint32_t os = 0, oph = 0, acc = 0, aph = 0;
         const uint32_t idesc = idesc_f16_k(128, 128), idesc_w = idesc_f16_k(128, 256);   // d = 256: N = 256
-        bool row_open = false;
-        for (;;) {
+        bool row_open = false, stop = false;
+        while (!stop) {
             mbar_wait(&S.op_full[os], oph);
             tc_fence_after();
-            const uint32_t meta = S.meta_op[os];
-            if (meta & F_STOP) break;
-            if (meta & F_FIRST) {
-                mbar_wait(&S.acc_empty[acc], aph ^ 1u);
-                tc_fence_after();
-                row_open = false;
-            }
-            if (lane == 0) {
-                const int ksteps = (int)(meta & 0xffu);
-                const uint32_t neg = (meta & F_NEG) ? IDESC_NEGATE_A : 0u;
-                const uint32_t hi = s32(&S.op[os][0][0]), lo = s32(&S.op[os][1][0]);
-                for (int ks = 0; ks < ((ta.debug & 2) ? 0 : ksteps); ++ks) {
-                    const uint32_t acc0 = (row_open || ks > 0) ? 1u : 0u;
-                    // K = 16 = two 8-k chunks: LBO apart; neighbouring 8-feature core matrices 128 B apart (SBO)
-                    const uint64_t dh = smem_desc(hi + ks * 2 * LBO, LBO, 128);
-                    const uint64_t dl = smem_desc(lo + ks * 2 * LBO, LBO, 128);
-                    if (D == 128) {
-                        const uint32_t dcol = tmem + D * (1 + acc);
-                        mma_f16(dcol, dh, dh, idesc | neg, acc0);
-                        mma_f16(dcol, dh, dl, idesc | neg, 1u);
-                        mma_f16(dcol, dl, dh, idesc | neg, 1u);
-                    } else {
-                        // rows 0..127 x columns 0..255 -> tensor-memory columns [0, 256)
-                        mma_f16(tmem, dh, dh, idesc_w | neg, acc0);
-                        mma_f16(tmem, dh, dl, idesc_w | neg, 1u);
-                        mma_f16(tmem, dl, dh, idesc_w | neg, 1u);
-                        // rows 128..255 x columns 128..255 -> tensor-memory columns [256, 384): features 128.. start 16
-                        // core matrices (2048 B) into the slab
-                        const uint64_t eh = smem_desc(hi + ks * 2 * LBO + 2048, LBO, 128);
-                        const uint64_t el = smem_desc(lo + ks * 2 * LBO + 2048, LBO, 128);
-                        mma_f16(tmem + 256, eh, eh, idesc | neg, acc0);
-                        mma_f16(tmem + 256, eh, el, idesc | neg, 1u);
-                        mma_f16(tmem + 256, el, eh, idesc | neg, 1u);
-                    }
+#pragma unroll 1
+            for (int e = 0; e < PT; ++e) {
+                const uint32_t meta = S.meta_op[os][e];
+                if (meta & F_STOP) {
+                    stop = true;
+                    break;
                 }
-                mma_commit(&S.op_empty[os]);
-                if (meta & F_LAST) mma_commit(&S.acc_full[acc]);
+                if (meta & F_FIRST) {
+                    mbar_wait(&S.acc_empty[acc], aph ^ 1u);
+                    tc_fence_after();
+                    row_open = false;
+                }
+                if (lane == 0) {
+                    const int ksteps = (int)(meta & 0xffu);
+                    const uint32_t neg = (meta & F_NEG) ? IDESC_NEGATE_A : 0u;
+                    const uint32_t hi = s32(&S.op[os][e][0][0]), lo = s32(&S.op[os][e][1][0]);
+                    for (int ks = 0; ks < ((ta.debug & 2) ? 0 : ksteps); ++ks) {
+                        const uint32_t acc0 = (row_open || ks > 0) ? 1u : 0u;
+                        // K = 16 = two 8-k chunks: LBO apart; neighbouring 8-feature core matrices 128 B apart (SBO)
+                        const uint64_t dh = smem_desc(hi + ks * 2 * LBO, LBO, 128);
+                        const uint64_t dl = smem_desc(lo + ks * 2 * LBO, LBO, 128);
+                        if (D == 128) {
+                            const uint32_t dcol = tmem + D * (1 + acc);
+                            mma_f16(dcol, dh, dh, idesc | neg, acc0);
+                            mma_f16(dcol, dh, dl, idesc | neg, 1u);
+                            mma_f16(dcol, dl, dh, idesc | neg, 1u);
+                        } else {
+                            // rows 0..127 x columns 0..255 -> tensor-memory columns [0, 256)
+                            mma_f16(tmem, dh, dh, idesc_w | neg, acc0);
+                            mma_f16(tmem, dh, dl, idesc_w | neg, 1u);
+                            mma_f16(tmem, dl, dh, idesc_w | neg, 1u);
+                            // rows 128..255 x columns 128..255 -> tensor-memory columns [256, 384): features 128.. start 16
+                            // core matrices (2048 B) into the slab
+                            const uint64_t eh = smem_desc(hi + ks * 2 * LBO + 2048, LBO, 128);
+                            const uint64_t el = smem_desc(lo + ks * 2 * LBO + 2048, LBO, 128);
+                            mma_f16(tmem + 256, eh, eh, idesc | neg, acc0);
+                            mma_f16(tmem + 256, eh, el, idesc | neg, 1u);
+                            mma_f16(tmem + 256, el, eh, idesc | neg, 1u);
+                        }
+                    }
+                    if (meta & F_LAST) mma_commit(&S.acc_full[acc]);
+                }
+                __syncwarp();
+                row_open = true;
+                if (meta & F_LAST) {
+                    if (++acc == NACC) { acc = 0; aph ^= 1u; }
+                }
             }
+            if (lane == 0) mma_commit(&S.op_empty[os]);   // (after a stop nobody waits for it any more)
             __syncwarp();
-            row_open = true;
-            if (meta & F_LAST) {
-                if (++acc == NACC) { acc = 0; aph ^= 1u; }
-            }
             if (++os == NO) { os = 0; oph ^= 1u; }
         }
     } else if (warp >= W_CONV && warp < W_CONV + N_CONV) {
@@ -457,136 +478,143 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         float wacc = 0.f;
 #pragma unroll
         for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
-        // Gathers.  The convert warps issue the tile gathers themselves, GATHER_AHEAD tiles before they consume the tile:
+        // Gathers.  The convert warps issue the gathers themselves, GATHER_AHEAD groups before they consume the group:
         // warp cw copies the TILE / 8 rows cw, cw + 8, ... of a planned tile with one coalesced 16-byte-per-lane cp.async per
         // 512 bytes (SASS LDGSTS; a whole warp instruction moves a full row segment, and the issue cost is spread over
         // eight warps that have issue slots to spare -- the 512-byte TMA bulk copies this replaces cost ~63-100 issue
         // cycles each in a dedicated warp) as one commit group per tile; before converting tile t a warp
         // waits for its own group of tile t (cp.async.wait_group) and posts one arrival on the tile's mbarrier.
         const int cw = cta >> 5;
-        uint32_t gs = 0, gph = 0, grs = 0, grph = 0;   // plan slot / raw stage of the next tile to gather
+        uint32_t gs = 0, gph = 0, grs = 0, grph = 0;   // plan group slot / raw stage of the next group to gather
         bool plan_end = false;
         auto gather = [&]() {
             if (plan_end) {
-                cp_async_commit();   // keep one commit group per iteration so that wait_group counts tiles to the very end
+                cp_async_commit();   // keep one commit group per iteration so that wait_group counts groups to the very end
                 return;
             }
             mbar_wait(&S.plan_full[gs], gph);
-            const uint32_t gmeta = S.meta_raw[gs];
-            mbar_wait(&S.raw_empty[grs], grph ^ 1u);   // every convert warp is done with the tile that used this stage
-            if (gmeta & F_STOP) {
-                plan_end = true;
-            } else {
-                const int gcnt = (ta.debug & 1) ? 0 : (int)(gmeta & 0xffu);
+            mbar_wait(&S.raw_empty[grs], grph ^ 1u);   // every convert warp is done with the group that used this stage
 #pragma unroll
-                for (int i = 0; i < TILE / 8; ++i) {
-                    const int slot = cw + 8 * i;
-                    if (slot < gcnt) {
-                        const float* src = a.Y + (int64_t)S.keys[gs][slot] * a.ld + lane * 4;
-                        float* dst = &S.raw[grs][slot * D + lane * 4];
+            for (int e = 0; e < PT; ++e) {
+                const uint32_t gmeta = S.meta_raw[gs * PT + e];
+                if (gmeta & F_STOP) {
+                    plan_end = true;
+                } else {
+                    const int gcnt = (ta.debug & 1) ? 0 : (int)(gmeta & 0xffu);
 #pragma unroll
-                        for (int c = 0; c < D / 128; ++c) cp_async16_cg(dst + c * 128, src + c * 128);
+                    for (int i = 0; i < TILE / 8; ++i) {
+                        const int slot = cw + 8 * i;
+                        if (slot < gcnt) {
+                            const float* src = a.Y + (int64_t)S.keys[gs * PT + e][slot] * a.ld + lane * 4;
+                            float* dst = &S.raw[grs][e][slot * D + lane * 4];
+#pragma unroll
+                            for (int c = 0; c < D / 128; ++c) cp_async16_cg(dst + c * 128, src + c * 128);
+                        }
                     }
                 }
             }
             cp_async_commit();
-            if (++gs == NP) { gs = 0; gph ^= 1u; }
+            if (++gs == NPG) { gs = 0; gph ^= 1u; }
             if (++grs == NR) { grs = 0; grph ^= 1u; }
         };
-        uint32_t cs = 0;   // plan slot of the tile being converted
+        uint32_t cs = 0;   // plan group slot of the group being converted
+        bool done = false;
 #pragma unroll 1
         for (int i = 0; i < GATHER_AHEAD; ++i) gather();
-        for (;;) {
+        while (!done) {
             gather();
-            cp_async_wait_group<GATHER_AHEAD>();   // this warp's rows of the tile about to be converted have landed
+            cp_async_wait_group<GATHER_AHEAD>();   // this warp's rows of the group about to be converted have landed
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.raw_full[rs]);
             mbar_wait(&S.raw_full[rs], rph);        // ... and everybody else's
-            const uint32_t meta = S.meta_raw[cs];
             mbar_wait(&S.op_empty[os], oph ^ 1u);
-            if (meta & F_STOP) {
-                if (cta == 0) S.meta_op[os] = F_STOP;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.op_full[os]);
-                break;
-            }
-            const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 15) >> 4;
-            if (meta & F_FIRST) {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
-                wacc = 0.f;
-            }
-            const float* rawp = &S.raw[rs][0];
-            unsigned char* hi = &S.op[os][0][0];
-            unsigned char* lo = &S.op[os][1][0];
-            // one chunk = 8 consecutive entries k of this thread's feature(s): a 16-byte group of the head and of the tail
-            // slab.  GUARD: the tile is not full -- slots >= cnt hold stale rows (scale and weight 0 from the planner; the
-            // value is zeroed as well so that a stale Inf/NaN cannot leak into an unrelated row).
-            auto chunk = [&](auto guard, const int kc) {
-                constexpr bool GUARD = decltype(guard)::value;
-                const int k0 = kc * 8;
-                const float4 sa = *reinterpret_cast<const float4*>(&S.sws[cs][k0]);
-                const float4 sb = *reinterpret_cast<const float4*>(&S.sws[cs][k0 + 4]);
-                const float4 wa = *reinterpret_cast<const float4*>(&S.wv[cs][k0]);
-                const float4 wb = *reinterpret_cast<const float4*>(&S.wv[cs][k0 + 4]);
-                if (LOSS1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const int m = ct + 128 * f;
-                    float q[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
-                    if (GUARD) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
-                    }
-                    const float2 q01 = make_float2(q[0], q[1]), q23 = make_float2(q[2], q[3]);
-                    const float2 q45 = make_float2(q[4], q[5]), q67 = make_float2(q[6], q[7]);
-                    uint4 h4, l4;
-                    split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
-                    split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
-                    split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
-                    split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
-                    const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
-                    *reinterpret_cast<uint4*>(hi + off) = h4;
-                    *reinterpret_cast<uint4*>(lo + off) = l4;
-                    bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
-                    bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
-                    bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
-                    bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
-                    if (LOSS1) {
-                        qacc[f].x += (q[0] + q[2]) + (q[4] + q[6]);
-                        qacc[f].y += (q[1] + q[3]) + (q[5] + q[7]);
-                    }
+#pragma unroll 1
+            for (int e = 0; e < PT; ++e) {
+                const uint32_t psl = cs * PT + e;   // the tile's plan slot
+                const uint32_t meta = S.meta_raw[psl];
+                if (meta & F_STOP) {
+                    if (cta == 0) S.meta_op[os][e] = F_STOP;
+                    done = true;
+                    break;
                 }
-            };
-            if (ta.debug & 4) {
-            } else if (cnt == TILE) {   // full tile: straight-line code
+                const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 15) >> 4;
+                if (meta & F_FIRST) {
 #pragma unroll
-                for (int c = 0; c < CHS; ++c) chunk(std::false_type{}, kh * CHS + c);
-            } else {
+                    for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
+                    wacc = 0.f;
+                }
+                const float* rawp = &S.raw[rs][e][0];
+                unsigned char* hi = &S.op[os][e][0][0];
+                unsigned char* lo = &S.op[os][e][1][0];
+                // one chunk = 8 consecutive entries k of this thread's feature(s): a 16-byte group of the head and of the
+                // tail slab.  GUARD: the tile is not full -- slots >= cnt hold stale rows (scale and weight 0 from the
+                // planner; the value is zeroed as well so that a stale Inf/NaN cannot leak into an unrelated row).
+                auto chunk = [&](auto guard, const int kc) {
+                    constexpr bool GUARD = decltype(guard)::value;
+                    const int k0 = kc * 8;
+                    const float4 sa = *reinterpret_cast<const float4*>(&S.sws[psl][k0]);
+                    const float4 sb = *reinterpret_cast<const float4*>(&S.sws[psl][k0 + 4]);
+                    const float4 wa = *reinterpret_cast<const float4*>(&S.wv[psl][k0]);
+                    const float4 wb = *reinterpret_cast<const float4*>(&S.wv[psl][k0 + 4]);
+                    if (LOSS1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
 #pragma unroll
-                for (int c = 0; c < CHS; ++c)
-                    if (kh * CHS + c < 2 * ksteps) chunk(std::true_type{}, kh * CHS + c);
+                    for (int f = 0; f < NF; ++f) {
+                        const int m = ct + 128 * f;
+                        float q[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
+                        if (GUARD) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
+                        }
+                        const float2 q01 = make_float2(q[0], q[1]), q23 = make_float2(q[2], q[3]);
+                        const float2 q45 = make_float2(q[4], q[5]), q67 = make_float2(q[6], q[7]);
+                        uint4 h4, l4;
+                        split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
+                        split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
+                        split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
+                        split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
+                        const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
+                        *reinterpret_cast<uint4*>(hi + off) = h4;
+                        *reinterpret_cast<uint4*>(lo + off) = l4;
+                        bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
+                        bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
+                        if (LOSS1) {
+                            qacc[f].x += (q[0] + q[2]) + (q[4] + q[6]);
+                            qacc[f].y += (q[1] + q[3]) + (q[5] + q[7]);
+                        }
+                    }
+                };
+                if (ta.debug & 4) {
+                } else if (cnt == TILE) {   // full tile: straight-line code
+#pragma unroll
+                    for (int c = 0; c < CHS; ++c) chunk(std::false_type{}, kh * CHS + c);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CHS; ++c)
+                        if (kh * CHS + c < 2 * ksteps) chunk(std::true_type{}, kh * CHS + c);
+                }
+                if (meta & F_LAST) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        S.bvec[bslot][kh][ct + 128 * f] = bacc[f].x + bacc[f].y;
+                        if (LOSS1) S.sumq[bslot][kh][ct + 128 * f] = qacc[f].x + qacc[f].y;
+                    }
+                    if (LOSS1 && ct == 0) S.wsum[bslot][kh] = wacc;
+                    bslot = (bslot + 1) & (NBV - 1);
+                }
+                if (cta == 0) S.meta_op[os][e] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
             }
             fence_proxy_async_smem();     // this thread's operand stores -> visible to the tensor core's (async proxy) reads
-            if (meta & F_LAST) {
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    S.bvec[bslot][kh][ct + 128 * f] = bacc[f].x + bacc[f].y;
-                    if (LOSS1) S.sumq[bslot][kh][ct + 128 * f] = qacc[f].x + qacc[f].y;
-                }
-                if (LOSS1 && ct == 0) S.wsum[bslot][kh] = wacc;
-                bslot = (bslot + 1) & (NBV - 1);
-            }
-            if (cta == 0) S.meta_op[os] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
             __syncwarp();
-            if (lane == 0) {   // one arrival per warp on each of the three hand-offs of a tile
+            if (lane == 0) {   // one arrival per warp on each of the three hand-offs of a group
                 mbar_arrive(&S.raw_empty[rs]);
                 mbar_arrive(&S.plan_empty[cs]);
                 mbar_arrive(&S.op_full[os]);
             }
-            cs = (cs + 1) & (NP - 1);
+            cs = (cs + 1) & (NPG - 1);
             if (++rs == NR) { rs = 0; rph ^= 1u; }
             if (++os == NO) { os = 0; oph ^= 1u; }
         }
