@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         bool row_open = false, stop = false;
         while (!stop) {
             mbar_wait(&S.op_full[os], oph);
+            fence_proxy_async_smem();   // the convert warps' generic-proxy operand stores -> visible to the tensor core's reads
             tc_fence_after();
 #pragma unroll 1
             for (int e = 0; e < PT; ++e) {
@@ -607,7 +608,9 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 }
                 if (cta == 0) S.meta_op[os][e] = (uint32_t)ksteps | (meta & (F_FIRST | F_LAST | F_NEG));
             }
-            fence_proxy_async_smem();     // this thread's operand stores -> visible to the tensor core's (async proxy) reads
+            // (no proxy fence here: FENCE.VIEW.ASYNC in a thread with cp.async / global loads in flight waits for them -- the
+            // next groups' gathers -- so the generic->async proxy fence is executed by the MMA-issuing warp after it has
+            // acquired the group through op_full)
             __syncwarp();
             if (lane == 0) {   // one arrival per warp on each of the three hand-offs of a group
                 mbar_arrive(&S.raw_empty[rs]);
