@@ -528,15 +528,28 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.raw_full[rs]);
             mbar_wait(&S.raw_full[rs], rph);        // ... and everybody else's
+            // all of this thread's values of the group are read up front (independent loads, one exposed latency per group instead
+            // of one per 8-entry chunk); unused slots read stale data that the guarded path zeroes
+            float qv[PT][CHS * 8 * NF];
+#pragma unroll
+            for (int e = 0; e < PT; ++e)
+#pragma unroll
+                for (int c = 0; c < CHS; ++c)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+#pragma unroll
+                        for (int f = 0; f < NF; ++f)
+                            qv[e][(c * 8 + i) * NF + f] = S.raw[rs][e][((kh * CHS + c) * 8 + i) * D + ct + 128 * f];
             mbar_wait(&S.op_empty[os], oph ^ 1u);
-#pragma unroll 1
+#pragma unroll
             for (int e = 0; e < PT; ++e) {
+                if (done) continue;
                 const uint32_t psl = cs * PT + e;   // the tile's plan slot
                 const uint32_t meta = S.meta_raw[psl];
                 if (meta & F_STOP) {
                     if (cta == 0) S.meta_op[os][e] = F_STOP;
                     done = true;
-                    break;
+                    continue;
                 }
                 const int cnt = (int)(meta & 0xffu), ksteps = (cnt + 15) >> 4;
                 if (meta & F_FIRST) {
@@ -544,15 +557,14 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                     for (int f = 0; f < NF; ++f) { bacc[f] = make_float2(0.f, 0.f); qacc[f] = make_float2(0.f, 0.f); }
                     wacc = 0.f;
                 }
-                const float* rawp = &S.raw[rs][e][0];
                 unsigned char* hi = &S.op[os][e][0][0];
                 unsigned char* lo = &S.op[os][e][1][0];
                 // one chunk = 8 consecutive entries k of this thread's feature(s): a 16-byte group of the head and of the
                 // tail slab.  GUARD: the tile is not full -- slots >= cnt hold stale rows (scale and weight 0 from the
                 // planner; the value is zeroed as well so that a stale Inf/NaN cannot leak into an unrelated row).
-                auto chunk = [&](auto guard, const int kc) {
+                auto chunk = [&](auto guard, const int c) {
                     constexpr bool GUARD = decltype(guard)::value;
-                    const int k0 = kc * 8;
+                    const int kc = kh * CHS + c, k0 = kc * 8;
                     const float4 sa = *reinterpret_cast<const float4*>(&S.sws[psl][k0]);
                     const float4 sb = *reinterpret_cast<const float4*>(&S.sws[psl][k0 + 4]);
                     const float4 wa = *reinterpret_cast<const float4*>(&S.wv[psl][k0]);
@@ -563,7 +575,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         const int m = ct + 128 * f;
                         float q[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) q[i] = rawp[(k0 + i) * D + m];
+                        for (int i = 0; i < 8; ++i) q[i] = qv[e][(c * 8 + i) * NF + f];
                         if (GUARD) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) q[i] = (k0 + i < cnt) ? q[i] : 0.f;
@@ -591,11 +603,11 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 if (ta.debug & 4) {
                 } else if (cnt == TILE) {   // full tile: straight-line code
 #pragma unroll
-                    for (int c = 0; c < CHS; ++c) chunk(std::false_type{}, kh * CHS + c);
+                    for (int c = 0; c < CHS; ++c) chunk(std::false_type{}, c);
                 } else {
 #pragma unroll
                     for (int c = 0; c < CHS; ++c)
-                        if (kh * CHS + c < 2 * ksteps) chunk(std::true_type{}, kh * CHS + c);
+                        if (kh * CHS + c < 2 * ksteps) chunk(std::true_type{}, c);
                 }
                 if (meta & F_LAST) {
 #pragma unroll
