@@ -24,9 +24,9 @@ def launches(path, traffic_json=None):
             v = v / 1e6 if r[iu] in ("nsecond", "ns") else (v / 1e3 if r[iu] in ("usecond", "us") else v)  # -> ms
         else:
             v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(r[iu], 1.0)
-        name = r[ik].split("(")[0].replace("void ", "").replace("bfl::", "")
+        name = r[ik].split("(")[0].replace("void ", "").replace("bfl::", "").replace("tc::", "")
         per.setdefault(r[iid], {"name": name})[r[im]] = v
-    ours_prefixes = ("als_", "gram_", "fast_", "bpr_", "warp_", "sgd_", "probe_")
+    ours_prefixes = ("als_", "gram_", "fast_", "bpr_", "warp_", "sgd_", "probe_", "tc_")
     agg = OrderedDict()
     for d in per.values():
         name = d["name"] if d["name"].startswith(ours_prefixes) else "torch (workload generation)"
