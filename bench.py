@@ -117,39 +117,67 @@ def make_workload_zipf(w, device, seed=2027):
     mu = np.log(mean_deg * inflate) - 0.5 * sigma * sigma
     deg = torch.exp(torch.randn(U, device=device, generator=g, dtype=torch.float32) * sigma + mu)
     deg = torch.clamp(deg, max=float(I) / 4).round().to(torch.int64)
-    draws = int(deg.sum().item())
     cdf = torch.cumsum(pmf, 0).to(torch.float32)
     cdf[-1] = 1.0
-    rows = torch.repeat_interleave(torch.arange(U, device=device, dtype=torch.int64), deg)
-    key = torch.empty(draws, device=device, dtype=torch.int64)
-    step = 1 << 28
-    for s0 in range(0, draws, step):
-        u = torch.rand(min(step, draws - s0), device=device, generator=g, dtype=torch.float32)
+    # torch.sort takes < 2^31 elements: the rowwise CSR is generated in user ranges of <= 2^29 draws (rows partition the
+    # key space, so sorted ranges concatenate), the colwise CSR by item ranges of the finished matrix
+    LIMIT = int(w.get("_chunk_limit", 1 << 29))
+    cum = torch.cumsum(deg, 0)
+    draws = int(cum[-1].item())
+    r_keys_parts, r_cnt_parts = [], []
+    u0 = 0
+    while u0 < U:
+        base = int(cum[u0 - 1].item()) if u0 else 0
+        u1 = int(torch.searchsorted(cum, torch.tensor([base + LIMIT], device=device, dtype=cum.dtype)).item())
+        u1 = min(max(u1, u0 + 1), U)
+        dg = deg[u0:u1]
+        n = int(dg.sum().item())
+        rows = torch.repeat_interleave(torch.arange(u0, u1, device=device, dtype=torch.int64), dg)
+        u = torch.rand(n, device=device, generator=g, dtype=torch.float32)
         col = torch.searchsorted(cdf, u).clamp_(max=I - 1)
-        key[s0:s0 + len(u)] = rows[s0:s0 + len(u)] * I + col
-        del u, col
-    del rows, deg
-    key = torch.sort(key).values
-    key = torch.unique_consecutive(key)
-    nnz = int(key.numel())
-    r_keys = (key % I).to(torch.int32)
-    rows = key // I
-    del key
-    r_indptr = torch.cumsum(torch.bincount(rows, minlength=U), 0)
-    key2 = r_keys.to(torch.int64) * U + rows
-    del rows
-    key2 = torch.sort(key2).values
-    c_keys = (key2 % U).to(torch.int32)
-    c_cols = key2 // U
-    del key2
-    c_indptr = torch.cumsum(torch.bincount(c_cols, minlength=I), 0)
-    del c_cols
+        del u
+        key = rows * I + col
+        del rows, col
+        key = torch.unique_consecutive(torch.sort(key).values)
+        r_keys_parts.append((key % I).to(torch.int32))
+        r_cnt_parts.append(torch.bincount(key // I - u0, minlength=u1 - u0))
+        del key
+        u0 = u1
+    r_keys = torch.cat(r_keys_parts)
+    del r_keys_parts
+    r_indptr = torch.cumsum(torch.cat(r_cnt_parts), 0)
+    del r_cnt_parts, cum, deg
+    nnz = int(r_keys.numel())
+    # colwise: item degrees, then per item range a stable sort of the range's entries by item (they are met in row order)
+    c_cnt = torch.zeros(I, device=device, dtype=torch.int64)
+    for s0 in range(0, nnz, 1 << 30):
+        c_cnt += torch.bincount(r_keys[s0:s0 + (1 << 30)].to(torch.int64), minlength=I)
+    c_indptr = torch.cumsum(c_cnt, 0)
+    c_keys = torch.empty(nnz, device=device, dtype=torch.int32)
+    i0 = 0
+    while i0 < I:
+        base = int(c_indptr[i0 - 1].item()) if i0 else 0
+        i1 = int(torch.searchsorted(c_indptr, torch.tensor([base + LIMIT], device=device, dtype=c_indptr.dtype)).item())
+        i1 = min(max(i1, i0 + 1), I)
+        end = int(c_indptr[i1 - 1].item())
+        idx_parts = []
+        for s0 in range(0, nnz, 1 << 30):   # positions (in row order) of the entries whose item lies in [i0, i1)
+            seg = r_keys[s0:s0 + (1 << 30)]
+            idx_parts.append(torch.nonzero((seg >= i0) & (seg < i1)).flatten() + s0)
+        idx = torch.cat(idx_parts)
+        del idx_parts
+        order = torch.sort(r_keys[idx], stable=True).indices
+        idx = idx[order]
+        del order
+        c_keys[base:end] = torch.searchsorted(r_indptr, idx, right=True).to(torch.int32)   # row of entry position idx
+        del idx
+        i0 = i1
     vals = torch.ones(nnz, device=device, dtype=torch.float32)
     if device.type == "cuda":
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
     return dict(U=U, I=I, nnz=nnz, r_indptr=r_indptr, r_keys=r_keys, c_indptr=c_indptr, c_keys=c_keys, vals=vals,
-                inflate=inflate)
+                inflate=inflate, draws=draws)
 
 
 def init_factors_t(rows, d, device, seed):

@@ -197,13 +197,15 @@ int solve_rows(bfl_als* h, int axis, int64_t row_begin, int64_t row_end, const i
         const int32_t* left = nullptr;
         int64_t nleft = 0;
         // d = 128: classes tcmin..5 (33..1536 nnz) on the fused tensor-core kernel, classes 6, 7 (longer) in its split-row
-        // mode; d = 256: class 7 (beyond the SIMT kernels' 12288 cap) in split-row mode
+        // mode; d = 256: classes 6, 7 (beyond 1536 nnz) in split-row mode
         int tcmin = FAST_NCLASS, splitmin = FAST_NCLASS;
         if (h->kernel_mode == 0 && tc::tc_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
             tcmin = h->tc_min_class;
             splitmin = 6;
         } else if (h->kernel_mode == 0 && tc::tc_split_applicable(h->optimizer_code, h->d, h->vdim, h->block_size)) {
-            splitmin = FAST_NCLASS - 1;
+            // d = 256: the re-gathering SIMT class (1537..12288 nnz) reads every gathered row 48 times (8 blocks x 6 passes);
+            // the split-row mode reads it once and pays 2 x 256 KB of scratch traffic per row instead
+            splitmin = 6;
         }
         int rc = fast_als_launch(a, h->fast_cache, h->num_sms, st, &left, &nleft, tcmin, splitmin, h->kernel_mode == 4 ? 1 : 0);
         if (rc != BFL_OK || nleft == 0) return rc;
