@@ -153,19 +153,19 @@ def main(args):
     value = nnz * steps / (ms / 1e3)
     peak, peak_src = bench.measured_peak()
     alg = algorithmic_bytes(algo, d, nnz, U, I, optimizer, mean_trials if mean_trials is not None else 2.0)
-    achieved = alg * steps / (ms / 1e3) / 1e9
+    achieved = alg * steps / (ms / 1e3) / 1e9 / world      # per GPU (every rank streams its own share)
     tfile = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     traffic = json.load(open(tfile)) if (world == 1 and os.path.isfile(tfile)) else None
     out = {"metric": "positives/sec (nnz/s) %s d=%d" % ("BPRMF" if algo == "bpr" else "WARP", d), "value": value,
            "unit": "nnz/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["desc"], "users": U, "items": I, "nnz": nnz, "d": d, "optimizer": optimizer,
-                      "max_trials": opt["max_trials"], "parallelism": "users sharded by nonzeros x%d" % world,
+                      "max_trials": opt.get("max_trials"), "parallelism": "users sharded by nonzeros x%d" % world,
                       "l2_policy": "factor matrices + CSR larger than L2 (C3); C4: Q is L2-resident by design"},
            "gpu_launches": int(launches), "clocks": clocks, "finite": finite,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": (traffic or {}).get("dram_bytes_per_epoch"), "traffic_source": (traffic or {}).get("source"),
-                        "peak_source": peak_src, "kernel": "epoch (sample + apply / accumulate + optimizer)",
+                        "peak_source": peak_src, "kernel": "epoch (sample + apply / accumulate + optimizer), per GPU",
                         "algorithmic_bytes_per_epoch": alg,
                         "note": "WARP C4: Q (25.6 MB) is L2-resident; the bound is L2 latency + RNG, not HBM" if algo == "warp" else
                                 "user rows counted once per user (a warp walks one user's positives back to back)"},
@@ -288,7 +288,7 @@ def reference_arm(args, w, threads, tinfo):
            "ms_per_step": w["nnz"] / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["desc"], "users": w["users"], "items": w["items"], "nnz": w["nnz"], "d": d,
-                      "optimizer": opt["optimizer"], "max_trials": opt["max_trials"], "sampled": cb["sample"]},
+                      "optimizer": opt["optimizer"], "max_trials": opt.get("max_trials"), "sampled": cb["sample"]},
            "cpu_baseline": cb, "e2e": {"value": v, "unit": "nnz/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out), flush=True)

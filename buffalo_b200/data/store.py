@@ -2,7 +2,6 @@
 File(path, "r"|"w"), attrs, create_group, create_dataset, `name in f`, keys(), dataset slicing / assignment,
 .shape, .chunks, close().  h5py is not installed in this image; the on-disk format is one uncompressed .npz
 written to exactly `path` (caching is keyed on os.path.isfile(opt.data.path), buffalo/data/mm.py:241-245)."""
-import io
 import json
 import os
 
@@ -82,11 +81,9 @@ class File(Group):
             arrays, attrs = {}, {}
             self._walk(self, "", arrays, attrs)
             arrays["__meta__"] = np.frombuffer(json.dumps(attrs).encode("utf-8"), dtype=np.uint8)
-            buf = io.BytesIO()
-            np.savez(buf, **arrays)
             tmp = self.path + ".tmp"
-            with open(tmp, "wb") as fout:
-                fout.write(buf.getvalue())
+            with open(tmp, "wb") as fout:      # straight to the file: no in-memory copy of a billion-entry database
+                np.savez(fout, **arrays)
             os.replace(tmp, self.path)
             self.mode = "closed"
 
