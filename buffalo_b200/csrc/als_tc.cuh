@@ -112,7 +112,7 @@ struct TcArgs {
     const int32_t* items;   // PARTIAL: triples (row, chunk, scratch slot)
     float* scratch;         // PARTIAL: per slot D*D matrix + D (b) + D (sum q) + 4 (sum w, ...) floats
     int64_t split;          // PARTIAL: chunk length in nnz
-    int debug;              // BFL_TC_DEBUG (timing experiments only; results are wrong): 1 no gathers, 2 no MMAs, 4 no convert math, 8 no epilogue math
+    int debug;              // BFL_TC_DEBUG (timing experiments only; results are wrong): 1 no gathers, 2 no MMAs, 4 no convert math, 8 no epilogue math, 16 planner only
 };
 
 template <int D>
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         uint32_t gsl = 0, rph = 0, pe = 0;   // group slot, phase of plan_empty, tile within the group
         // begin a tile: its plan slot (the group's slots are claimed when its first tile starts)
         auto tile_begin = [&]() -> uint32_t {
-            if (pe == 0) mbar_wait(&S.plan_empty[gsl], rph ^ 1u);
+            if (pe == 0) mbar_wait_idle(&S.plan_empty[gsl], rph ^ 1u);
             return gsl * PT + pe;
         };
         // finish a tile (after __syncwarp): the group is published with its last tile
@@ -520,8 +520,23 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
         };
         uint32_t cs = 0;   // plan group slot of the group being converted
         bool done = false;
+        if (ta.debug & 16) {   // timing experiment: consume the plans as fast as they come, nothing else
+            uint32_t ph = 0;
+            for (;;) {
+                mbar_wait(&S.plan_full[cs], ph);
+                const bool stop = (S.meta_raw[cs * PT] | S.meta_raw[cs * PT + 1]) & F_STOP;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.plan_empty[cs]);
+                if (stop) break;
+                if (++cs == NPG) { cs = 0; ph ^= 1u; }
+            }
+            if (cta == 0) S.meta_op[0][0] = F_STOP;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.op_full[0]);
+            done = true;
+        }
 #pragma unroll 1
-        for (int i = 0; i < GATHER_AHEAD; ++i) gather();
+        for (int i = 0; i < GATHER_AHEAD && !done; ++i) gather();
         while (!done) {
             gather();
             cp_async_wait_group<GATHER_AHEAD>();   // this warp's rows of the group about to be converted have landed
@@ -652,7 +667,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 if (nit < nitems) item_info(nit, nrow, nbeg, nn, nslot);
                 const uint32_t acc = (uint32_t)(seq % NACC), aph = (uint32_t)((seq / NACC) & 1);
                 const uint32_t bs = (uint32_t)(seq & (NBV - 1));
-                mbar_wait(&S.acc_full[acc], aph);
+                mbar_wait_idle(&S.acc_full[acc], aph);
                 tc_fence_after();
                 float* sc = ta.scratch + (size_t)slot * scratch_floats<D>();
                 if constexpr (D == 128) {
@@ -709,7 +724,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 if (row < 0 || !a.compute_loss) return 0.f;
                 return (float)(a.indptr[row] - (row == 0 ? 0 : a.indptr[row - 1]));
             };
-            int row = row_of(0), row1 = row_of(1), row2 = row_of(2);
+            int row = (ta.debug & 16) ? -1 : row_of(0), row1 = row_of(1), row2 = row_of(2);
             float xj = row >= 0 ? a.X[(int64_t)row * a.ld + j] : 0.f;
             float x1 = row1 >= 0 ? a.X[(int64_t)row1 * a.ld + j] : 0.f;
             float nlen = len_of(row), nlen1 = len_of(row1);
@@ -733,7 +748,7 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                 const uint32_t xsl = (uint32_t)(seq & (NXS - 1));
                 const float* xs = S.xs[xsl];
                 mbar_wait(&S.x_full[xsl], (uint32_t)((seq / NXS) & 1));
-                mbar_wait(&S.acc_full[acc], aph);
+                mbar_wait_idle(&S.acc_full[acc], aph);
                 tc_fence_after();
                 if (ta.debug & 8) {
                     tc_fence_before();
