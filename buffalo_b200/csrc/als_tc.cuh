@@ -495,6 +495,24 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
             }
             mbar_wait(&S.plan_full[gs], gph);
             mbar_wait(&S.raw_empty[grs], grph ^ 1u);   // every convert warp is done with the group that used this stage
+            const uint32_t gm0 = S.meta_raw[gs * PT], gm1 = S.meta_raw[gs * PT + 1];
+            if (PT == 2 && !(ta.debug & 1) && ((gm0 | gm1) & F_STOP) == 0 && (gm0 & 0xffu) == TILE && (gm1 & 0xffu) == TILE) {
+                // two full tiles (the common case): straight-line copies, no per-row predicates
+                int32_t kk[PT][TILE / 8];
+#pragma unroll
+                for (int e = 0; e < PT; ++e)
+#pragma unroll
+                    for (int i = 0; i < TILE / 8; ++i) kk[e][i] = S.keys[gs * PT + e][cw + 8 * i];
+#pragma unroll
+                for (int e = 0; e < PT; ++e)
+#pragma unroll
+                    for (int i = 0; i < TILE / 8; ++i) {
+                        const float* src = a.Y + (int64_t)kk[e][i] * a.ld + lane * 4;
+                        float* dst = &S.raw[grs][e][(cw + 8 * i) * D + lane * 4];
+#pragma unroll
+                        for (int c = 0; c < D / 128; ++c) cp_async16_cg(dst + c * 128, src + c * 128);
+                    }
+            } else
 #pragma unroll
             for (int e = 0; e < PT; ++e) {
                 const uint32_t gmeta = S.meta_raw[gs * PT + e];
@@ -556,6 +574,70 @@ __global__ void __launch_bounds__(THREADS, 1) als_tc_kernel(TcArgs ta) {
                         for (int f = 0; f < NF; ++f)
                             qv[e][(c * 8 + i) * NF + f] = S.raw[rs][e][((kh * CHS + c) * 8 + i) * D + ct + 128 * f];
             mbar_wait(&S.op_empty[os], oph ^ 1u);
+            const uint32_t cm0 = S.meta_raw[cs * PT], cm1 = S.meta_raw[cs * PT + 1];
+            const bool fast2 = PT == 2 && !(ta.debug & 4) && ((cm0 | cm1) & F_STOP) == 0 && (cm0 & 0xffu) == TILE &&
+                               (cm1 & 0xffu) == TILE;
+            if (fast2) {
+                // Two full tiles: one straight-line block (the row bookkeeping is branch-free: the accumulators are reset by
+                // selects on F_FIRST, the partial sums are stored after EVERY tile and the slot only advances on F_LAST), so
+                // that the compiler can interleave the four chunks' load -> scale -> split -> store chains.
+#pragma unroll
+                for (int e = 0; e < PT; ++e) {
+                    const uint32_t meta = e == 0 ? cm0 : cm1;
+                    const uint32_t psl = cs * PT + e;
+                    const bool first = (meta & F_FIRST) != 0;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        bacc[f].x = first ? 0.f : bacc[f].x; bacc[f].y = first ? 0.f : bacc[f].y;
+                        qacc[f].x = first ? 0.f : qacc[f].x; qacc[f].y = first ? 0.f : qacc[f].y;
+                    }
+                    wacc = first ? 0.f : wacc;
+                    unsigned char* hi = &S.op[os][e][0][0];
+                    unsigned char* lo = &S.op[os][e][1][0];
+#pragma unroll
+                    for (int c = 0; c < CHS; ++c) {
+                        const int kc = kh * CHS + c, k0 = kc * 8;
+                        const float4 sa = *reinterpret_cast<const float4*>(&S.sws[psl][k0]);
+                        const float4 sb = *reinterpret_cast<const float4*>(&S.sws[psl][k0 + 4]);
+                        const float4 wa = *reinterpret_cast<const float4*>(&S.wv[psl][k0]);
+                        const float4 wb = *reinterpret_cast<const float4*>(&S.wv[psl][k0 + 4]);
+                        if (LOSS1) wacc += ((wa.x + wa.y) + (wa.z + wa.w)) + ((wb.x + wb.y) + (wb.z + wb.w));
+#pragma unroll
+                        for (int f = 0; f < NF; ++f) {
+                            const int m = ct + 128 * f;
+                            const float* q = &qv[e][0];
+                            const float2 q01 = make_float2(q[(c * 8 + 0) * NF + f], q[(c * 8 + 1) * NF + f]);
+                            const float2 q23 = make_float2(q[(c * 8 + 2) * NF + f], q[(c * 8 + 3) * NF + f]);
+                            const float2 q45 = make_float2(q[(c * 8 + 4) * NF + f], q[(c * 8 + 5) * NF + f]);
+                            const float2 q67 = make_float2(q[(c * 8 + 6) * NF + f], q[(c * 8 + 7) * NF + f]);
+                            uint4 h4, l4;
+                            split_f16x2(f2mul(q01, make_float2(sa.x, sa.y)), h4.x, l4.x);
+                            split_f16x2(f2mul(q23, make_float2(sa.z, sa.w)), h4.y, l4.y);
+                            split_f16x2(f2mul(q45, make_float2(sb.x, sb.y)), h4.z, l4.z);
+                            split_f16x2(f2mul(q67, make_float2(sb.z, sb.w)), h4.w, l4.w);
+                            const int off = kc * LBO + (m >> 3) * 128 + (m & 7) * 16;
+                            *reinterpret_cast<uint4*>(hi + off) = h4;
+                            *reinterpret_cast<uint4*>(lo + off) = l4;
+                            bacc[f] = f2fma(make_float2(wa.x, wa.y), q01, bacc[f]);
+                            bacc[f] = f2fma(make_float2(wa.z, wa.w), q23, bacc[f]);
+                            bacc[f] = f2fma(make_float2(wb.x, wb.y), q45, bacc[f]);
+                            bacc[f] = f2fma(make_float2(wb.z, wb.w), q67, bacc[f]);
+                            if (LOSS1) {
+                                qacc[f].x += (q01.x + q23.x) + (q45.x + q67.x);
+                                qacc[f].y += (q01.y + q23.y) + (q45.y + q67.y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        S.bvec[bslot][kh][ct + 128 * f] = bacc[f].x + bacc[f].y;
+                        if (LOSS1) S.sumq[bslot][kh][ct + 128 * f] = qacc[f].x + qacc[f].y;
+                    }
+                    if (LOSS1 && ct == 0) S.wsum[bslot][kh] = wacc;
+                    bslot = (bslot + ((meta & F_LAST) ? 1u : 0u)) & (NBV - 1);
+                    if (cta == 0) S.meta_op[os][e] = (uint32_t)(TILE / 16) | (meta & (F_FIRST | F_LAST | F_NEG));
+                }
+            } else
 #pragma unroll
             for (int e = 0; e < PT; ++e) {
                 if (done) continue;
