@@ -10,6 +10,6 @@ mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches_c2.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_launches_c2.stdout 2> gpurun_out/${TAG}_launches_c2.stderr
-ncu --set full --clock-control none --import-source on -k regex:als_ialspp_team -c 9 -f -o gpurun_out/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:als_tc_kernel --launch-skip 1 -c 2 -f -o gpurun_out/${TAG}_prof \
     python bench.py --workload c2_small --steps 1 --warmup 0 --no-e2e --no-cpu > gpurun_out/${TAG}_prof.stdout 2> gpurun_out/${TAG}_prof.stderr
 ls -la gpurun_out/ | tail -5

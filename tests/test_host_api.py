@@ -322,3 +322,30 @@ def test_csr_from_triples_device_sort_matches_host_sort():
             a = csr_from_triples(major, minor, vals, nm, stable_sort=stable)
             b = csr_from_triples(major, minor, vals, nm, stable_sort=stable, device="cpu")
             assert all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, b))
+
+
+def test_bench_zipf_generator_chunked_equals_unchunked():
+    """bench.py's C5 generator (Zipf items, de-duplicated per user) builds the matrix in ranges so that no sort
+    exceeds 2^31 elements at full scale; the ranges must not change the result, the rowwise CSR must be sorted and
+    duplicate-free, and the colwise CSR must be its exact transpose in (item, user) order."""
+    import torch
+    import bench
+    ref = None
+    for lim in (1 << 29, 4096, 777):
+        w = dict(users=2500, items=300, nnz=50000, d=32, zipf=1.1, _chunk_limit=lim)
+        wl = bench.make_workload_zipf(w, torch.device("cpu"))
+        U, I, nnz = wl["U"], wl["I"], wl["nnz"]
+        ri, rk = wl["r_indptr"].numpy(), wl["r_keys"].numpy()
+        ci, ck = wl["c_indptr"].numpy(), wl["c_keys"].numpy()
+        assert ri[-1] == nnz == ci[-1] and len(rk) == nnz == len(ck)
+        rows = np.repeat(np.arange(U), np.diff(np.concatenate([[0], ri])))
+        assert (np.diff(rows.astype(np.int64) * I + rk) > 0).all()           # sorted, no duplicates
+        order = np.lexsort((rows, rk))
+        assert (ck == rows[order]).all()
+        assert (np.diff(np.concatenate([[0], ci])) == np.bincount(rk, minlength=I)).all()
+        deg_items = np.bincount(rk, minlength=I)
+        assert deg_items[:10].mean() > 20 * max(1.0, deg_items[I // 2:].mean())   # a Zipf head
+        if ref is None:
+            ref = (ri.copy(), rk.copy(), ck.copy())
+        else:
+            assert (ref[0] == ri).all() and (ref[1] == rk).all() and (ref[2] == ck).all()
