@@ -18,7 +18,8 @@ struct bfl_als {
     int kernel_mode = 0;  // 0 auto (d = 128: tensor-core kernel als_tc.cuh for rows above tc_min_nnz, tuned SIMT kernels
                           // otherwise), 1 force generic, 2 tuned SIMT kernels only (the round-1 path), 4 SIMT only with
                           // rows of 513..1536 nnz on the re-gathering class
-    int tc_min_class = 1; // first row-length class (als_fast.cuh) solved by the tensor-core kernel
+    int tc_min_class = 2; // first row-length class (als_fast.cuh) solved by the tensor-core kernel (rows of <= 64 nnz stay on
+                          // the SIMT classes 0, 1: an epilogue per row costs more than their whole SIMT solve; measured 400 vs 411 ms)
 
     // factors: either owned device mirrors of retained host pointers, or borrowed device memory
     float* hostP = nullptr;
@@ -77,7 +78,7 @@ int als_apply_options(bfl_als* h, const JsonOpt& j) {
     h->eps = (float)j.number("eps", 1e-10);
     h->cg_tolerance = (float)j.number("cg_tolerance", 1e-10);
     h->kernel_mode = j.integer("_b200_kernel_mode", 0);
-    h->tc_min_class = std::max(0, std::min(7, j.integer("_b200_tc_min_class", 1)));
+    h->tc_min_class = std::max(0, std::min(7, j.integer("_b200_tc_min_class", 2)));
     std::string optimizer = j.string("optimizer", "manual_cg");
     if (h->d >= 128) optimizer = "ialspp";  // als.cc:46
     if (optimizer == "llt") h->optimizer_code = 0;
