@@ -498,7 +498,8 @@ def main():
                       "parallelism": ("row-sharded x%d, updated factor rows pushed to the peer replicas from inside the solve "
                                       "kernel (P2P stores over NVLink) + 1-element all-reduce as barrier" % world)
                       if (world > 1 and args.exchange == "p2p") else
-                      ("row-sharded x%d, NCCL all-gather of the updated factor shard per half-epoch" % world),
+                      ("row-sharded x%d, NCCL all-gather of the updated factor shard per half-epoch" % world) if world > 1
+                      else "single GPU",
                       "l2_policy": "inputs (>= 16 GB) larger than L2; no explicit flush"},
            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
 

@@ -1,6 +1,6 @@
-// Thin inline-PTX wrappers for the sm_100a features the tensor-core ALS kernel uses: mbarrier, 1-D bulk async
-// copies (TMA, SASS UBLKCP), tensor memory (tcgen05.alloc/ld, SASS LDTM) and tcgen05.mma kind::f16 / kind::tf32
-// (SASS UTCHMMA) with shared-memory matrix descriptors.  No CUTLASS: every string below is plain PTX ISA 8.8.
+// Thin inline-PTX wrappers for the sm_100a features the tensor-core ALS kernel uses: mbarrier, cp.async (SASS LDGSTS),
+// tensor memory (tcgen05.alloc/ld/st, SASS LDTM/STTM) and tcgen05.mma kind::f16 (SASS UTCHMMA) with shared-memory matrix
+// descriptors.  (The 1-D bulk-copy / TMA wrappers of the first version live on in benchmarks/gather_probe.cu.)  No CUTLASS: every string below is plain PTX ISA 8.8.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,9 +17,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -43,19 +40,10 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) __nanosleep(128);
 }
 
-// generic-proxy writes to shared memory -> visible to the async proxy (bulk copies, tensor-core operand reads)
+// generic-proxy writes to shared memory -> visible to the async proxy (tensor-core operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- 1-D bulk async copy global -> shared (TMA), completion on an mbarrier ----------------------
-// bytes % 16 == 0, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     s32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(s32(bar))
-                 : "memory");
-}
-
-// ---- 16-byte cp.async (SASS LDGSTS), completion counted on an mbarrier -------------------------------
+// ---- 16-byte cp.async (SASS LDGSTS), completion by commit / wait groups ---------------------------------
 __device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -91,16 +79,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }
