@@ -16,22 +16,26 @@
 // nothing overflows fp16 and entries down to 2^-20 of the largest keep a normal tail; the accumulator is multiplied by
 // 2^-2e (exact) when it is read.  b and the loss pieces are accumulated in plain fp32 from the unscaled rows.
 //
-// Pipeline of one persistent CTA (one per SM, 16 warps, warp-specialised, mbarrier hand-offs only):
+// Pipeline of one persistent CTA (one per SM, 14 warps x 128 registers, warp-specialised, mbarrier hand-offs only, one
+// elected arrival per warp; hand-offs are per GROUP of two consecutive tiles of the CTA's tile stream):
 //   planner warp     : walks the CTA's rows; every level of the dependent load chain (row id -> offsets -> keys / values)
 //                     is issued whole rows ahead of its use; per tile of 32 entries it writes the gather plan (keys,
-//                     2^e sqrt|w|, w, count / flags) into the tile's ring slot;
-//   6 issuer warps   : turn a plan into 512-byte cp.async.bulk copies (TMA, SASS UBLKCP) of the gathered opposite-factor
-//                     rows into the ring of raw fp32 tiles, completion by mbarrier expect_tx.  A divergent-address bulk
-//                     copy compiles to an ELECT / R2UR / UBLKCP loop over the lanes, ~63 cycles per copy and warp: one warp
-//                     alone sustains 2.3 TB/s chip-wide, two 4.7, four or more the 7.0 TB/s HBM read ceiling
-//                     (benchmarks/gather_probe.cu) -- so the copies of a tile are dealt round-robin to six warps that do
-//                     nothing else;
-//   4 convert warps  : thread m owns feature m: reads column m of the raw tile (conflict-free), scales, splits, and writes
-//                     16-byte groups of 8 consecutive k into the K-major un-swizzled operand slabs (8 x 16 B core
-//                     matrices); accumulates b_m = sum w q_m (exact fp32) and the loss pieces in registers;
-//   MMA warp         : one lane issues tcgen05.mma kind::f16 (M = N = 128, K = 16; SASS UTCHMMA), accumulating the row's
-//                     matrix in tensor memory; entries with negative weight travel in their own tiles and are
-//                     subtracted with the instruction descriptor's negate-A bit;
+//                     2^e sqrt|w|, w, count / flags) into a 16-slot ring -- it runs up to 8 groups ahead;
+//   8 convert warps  : (a) gathers: two hand-offs ahead of its use, warp cw copies the rows cw, cw + 8, ... of a planned
+//                     tile with one coalesced 16-byte-per-lane cp.async per 512 bytes (SASS LDGSTS) into a ring of raw fp32
+//                     tiles (commit / wait groups + one mbarrier arrival per warp).  The first version gathered with
+//                     512-byte cp.async.bulk copies (TMA): a divergent-address bulk copy compiles to an ELECT / R2UR / UBLKCP
+//                     loop over the lanes, ~63-100 cycles per copy and warp -- one warp sustains 2.3 TB/s chip-wide, four
+//                     or more the 7.0 TB/s HBM read ceiling (benchmarks/gather_probe.cu) -- so it needed six warps that
+//                     did nothing else; spread over the convert warps the cp.async issue is a few instructions per tile;
+//                     (b) convert: thread = (feature m, entry half): reads column m of the raw tile (conflict-free),
+//                     scales, splits, and writes 16-byte groups of 8 consecutive k into the K-major un-swizzled operand
+//                     slabs (8 x 16 B core matrices, conflict-free); accumulates b_m = sum w q_m (exact fp32) and the loss
+//                     pieces in registers; groups of two full tiles take a branch-free straight-line path;
+//   MMA warp         : executes the generic -> async proxy fence for the group it has acquired, then one lane issues
+//                     tcgen05.mma kind::f16 (M = N = 128, K = 16; SASS UTCHMMA), accumulating the row's matrix in tensor
+//                     memory; entries with negative weight travel in their own tiles and are subtracted with the
+//                     instruction descriptor's negate-A bit;
 //   4 epilogue warps : a systolic pipeline over rows.  Thread j owns matrix row j (tensor-memory lane j), warp q column
 //                     block q: tcgen05.ld (SASS LDTM) the accumulator and the resident G + reg*I (tensor memory columns
 //                     0..127), h = M x - b; then warp q folds the deltas of blocks 0..q-1 into its h as they are published,
