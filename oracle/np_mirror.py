@@ -123,3 +123,121 @@ def als_half_epoch(X, Y, indptr_end, keys, vals, opt, axis):
         else:
             raise ValueError(optimizer)
     return X, nume, deno
+
+
+# ---------------------------------------------------------------------------------------------------
+# BPRMF / WARP (fp64, written from lib/algo_impl/bpr/bpr.cc:119-188, lib/algo_impl/warp/warp.cc:30-52,137-163,
+# 192-226 -- NOT from buffalo_oracle.c) so that the C restatement of the update maths has an independent pin
+# ---------------------------------------------------------------------------------------------------
+def bpr_logit(x, max_exp=6.0):
+    """1 - sigmoid(x) with the reference's clamp (bpr.cc:123-131; the exact function, not the 1000-entry table)."""
+    if x > max_exp:
+        return 0.0
+    if x < -max_exp:
+        return 1.0
+    return 1.0 / (1.0 + np.exp(x))
+
+
+def bpr_accumulate(P, Q, Qb, users, positives, negatives, use_bias=True, update_i=True, update_j=True,
+                   per_coordinate_normalize=True, num_negative_samples=1):
+    """Gradient-accumulating optimizers (bpr.cc:138-156,172-179): P, Q are read-only, so the order of the triples
+    does not matter.  `users/positives/negatives` list one entry per (positive, negative draw)."""
+    P, Q, Qb = P.astype(np.float64), Q.astype(np.float64), Qb.astype(np.float64)
+    gP, gQ, gQb = np.zeros_like(P), np.zeros_like(Q), np.zeros_like(Qb)
+    cP, cQ = np.zeros(P.shape[0], np.int64), np.zeros(Q.shape[0], np.int64)
+    for t, (u, i, j) in enumerate(zip(users, positives, negatives)):
+        x = P[u] @ (Q[i] - Q[j]) + ((Qb[i, 0] - Qb[j, 0]) if use_bias else 0.0)
+        lg = bpr_logit(x)
+        if per_coordinate_normalize:
+            cQ[j] += 1
+        gP[u] += lg * (Q[i] - Q[j])
+        if update_i:
+            gQ[i] += lg * P[u]
+            if use_bias:
+                gQb[i, 0] += lg
+        if update_j:
+            gQ[j] -= lg * P[u]
+            if use_bias:
+                gQb[j, 0] -= lg
+        if per_coordinate_normalize and t % num_negative_samples == num_negative_samples - 1:   # once per positive
+            cP[u] += 1
+            cQ[i] += 1
+    return gP, gQ, gQb, cP, cQ
+
+
+def bpr_sgd(P, Q, Qb, users, positives, negatives, lr, reg_u, reg_i, reg_j, reg_b, use_bias=True, update_i=True,
+            update_j=True):
+    """Plain SGD, sequential (bpr.cc:157-171).  `g` is a lazy Eigen expression: the user row is updated with the ALREADY
+    updated item rows."""
+    P, Q, Qb = P.astype(np.float64).copy(), Q.astype(np.float64).copy(), Qb.astype(np.float64).copy()
+    for u, i, j in zip(users, positives, negatives):
+        x = P[u] @ (Q[i] - Q[j]) + ((Qb[i, 0] - Qb[j, 0]) if use_bias else 0.0)
+        lg = bpr_logit(x)
+        deriv = lg * P[u]
+        if update_i:
+            Q[i] += lr * (deriv - reg_i * Q[i])
+            if use_bias:
+                Qb[i, 0] += lr * (lg - reg_b * Qb[i, 0])
+        if update_j:
+            Q[j] += lr * (-deriv - reg_j * Q[j])
+            if use_bias:
+                Qb[j, 0] += lr * (-lg - reg_b * Qb[j, 0])
+        P[u] += lr * (lg * (Q[i] - Q[j]) - reg_u * P[u])
+    return P, Q, Qb
+
+
+def bpr_loss(P, Q, Qb, users, positives, negatives, use_bias=True):
+    """bpr.cc:227-244"""
+    P, Q, Qb = P.astype(np.float64), Q.astype(np.float64), Qb.astype(np.float64)
+    tot = 0.0
+    for u, i, j in zip(users, positives, negatives):
+        x = P[u] @ Q[i] - P[u] @ Q[j] + ((Qb[i, 0] - Qb[j, 0]) if use_bias else 0.0)
+        tot += np.log(1.0 + np.exp(-x))
+    return tot / len(users)
+
+
+def warp_accumulate(P, Q, indptr_end, keys, trials, negs, reg_u, reg_i, reg_j, threshold=1.0, score="dot"):
+    """Given the trace of the rank-sampling loop (trial count and violating negative per positive; 0 trials = discarded),
+    the accumulated gradients, sample counters and partial loss (warp.cc:30-52,150-163)."""
+    P, Q = P.astype(np.float64), Q.astype(np.float64)
+    I = Q.shape[0]
+    gP, gQ = np.zeros_like(P), np.zeros_like(Q)
+    cP, cQ = np.zeros(P.shape[0], np.int64), np.zeros(I, np.int64)
+    beg = np.concatenate([[0], indptr_end[:-1]])
+    rows = np.repeat(np.arange(len(indptr_end)), indptr_end - beg)
+    loss, updates = 0.0, 0
+
+    def sc(a, b):
+        return a @ b if score == "dot" else -((a - b) @ (a - b))
+    for k in range(len(keys)):
+        if trials[k] == 0:
+            continue
+        u, i, j = rows[k], keys[k], negs[k]
+        n_seen = int(indptr_end[u] - beg[u])
+        phi = np.log(max(1, int((I - n_seen - 1) // int(trials[k]))))
+        if score == "dot":
+            du, di, dj = phi * (Q[i] - Q[j]), phi * P[u], -phi * P[u]
+        else:
+            du, di, dj = phi * 2 * (Q[i] - Q[j]), phi * (P[u] - Q[i]), -phi * (P[u] - Q[j])
+        gP[u] += du - reg_u * P[u]
+        gQ[i] += di - reg_i * Q[i]
+        gQ[j] += dj - reg_j * Q[j]
+        cP[u] += 1
+        cQ[i] += 1
+        cQ[j] += 1
+        loss += sc(P[u], Q[j]) - sc(P[u], Q[i]) + threshold
+        updates += 1
+    return gP, gQ, cP, cQ, loss, updates
+
+
+def warp_project(F):
+    """rows are pulled back onto the unit ball (warp.cc:194-200)"""
+    F = F.astype(np.float64)
+    nrm = np.sqrt((F * F).sum(axis=1))
+    return F / np.maximum(1.0, nrm)[:, None]
+
+
+def warp_loss(P, Q, users, positives, negatives, threshold=1.0):
+    """fraction of probe triples that violate the margin (warp.cc:205-223)"""
+    P, Q = P.astype(np.float64), Q.astype(np.float64)
+    return float(np.mean([(P[u] @ Q[i] - P[u] @ Q[j]) < threshold for u, i, j in zip(users, positives, negatives)]))
