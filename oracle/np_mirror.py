@@ -237,7 +237,10 @@ def warp_project(F):
     return F / np.maximum(1.0, nrm)[:, None]
 
 
-def warp_loss(P, Q, users, positives, negatives, threshold=1.0):
+def warp_loss(P, Q, users, positives, negatives, threshold=1.0, score="dot"):
     """fraction of probe triples that violate the margin (warp.cc:205-223)"""
     P, Q = P.astype(np.float64), Q.astype(np.float64)
-    return float(np.mean([(P[u] @ Q[i] - P[u] @ Q[j]) < threshold for u, i, j in zip(users, positives, negatives)]))
+
+    def sc(a, b):
+        return a @ b if score == "dot" else -((a - b) @ (a - b))
+    return float(np.mean([(sc(P[u], Q[i]) - sc(P[u], Q[j])) < threshold for u, i, j in zip(users, positives, negatives)]))
